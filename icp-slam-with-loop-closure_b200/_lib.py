@@ -1,0 +1,105 @@
+"""ctypes binding of libicpb.so (include/icpb.h).  No CPU fallback: if the CUDA library is
+missing or no sm_100 device is present, every entry point raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libicpb.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destroy",
+           "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
+           "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error"]
+
+
+class IcpbParams(ctypes.Structure):
+    _fields_ = [("epsilon", ctypes.c_double), ("stopping_thresh", ctypes.c_double),
+                ("max_iters", ctypes.c_int32), ("rotation_only", ctypes.c_int32),
+                ("hist_cap", ctypes.c_int32), ("corr_stride", ctypes.c_int32),
+                ("pair_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("k_first", ctypes.c_int64), ("k_block", ctypes.c_int64), ("k_stride", ctypes.c_int64)]
+
+
+class IcpbKernelInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("threads_per_cta", "ctas_per_sm", "sm_count", "grid",
+                                              "regs_per_thread", "smem_bytes", "points_per_thread",
+                                              "variant")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class IcpbError(RuntimeError):
+    pass
+
+
+def sources():
+    c = os.path.join(_HERE, "csrc")
+    return [os.path.join(c, "icpb_api.cu")], [os.path.join(c, "icpb_kernels.cuh"),
+                                              os.path.join(_ROOT, "include", "icpb.h")]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libicpb.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs, deps = sources()
+    newest = max(os.path.getmtime(p) for p in srcs + deps)
+    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= newest:
+        return SO_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
+                                   "-o", SO_PATH] + srcs
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise IcpbError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = ctypes.CDLL(SO_PATH)
+    vp, i64, i32p, dp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p
+    L.icpb_default_params.argtypes = [ctypes.POINTER(IcpbParams)]
+    L.icpb_default_params.restype = None
+    L.icpb_abi_version.restype = ctypes.c_int
+    L.icpb_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.icpb_destroy.argtypes = [vp]
+    L.icpb_upload_scans.argtypes = [vp, dp, vp, i64]
+    L.icpb_set_scans_device.argtypes = [vp, dp, vp, i64, i64]
+    L.icpb_run_device.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p, vp]
+    L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
+    L.icpb_icp_pair_host.argtypes = [vp, dp, i64, dp, i64, dp, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
+    L.icpb_get_kernel_info.argtypes = [vp, i64, ctypes.POINTER(IcpbKernelInfo)]
+    L.icpb_launch_count.argtypes = [vp]
+    L.icpb_launch_count.restype = ctypes.c_int64
+    L.icpb_last_error.restype = ctypes.c_char_p
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().icpb_last_error().decode("utf-8", "replace")
+        if rc in (10001, 10002):
+            raise ValueError(f"{what}: {msg}")
+        raise IcpbError(f"{what}: status {rc}: {msg}")
+
+
+def default_params() -> IcpbParams:
+    p = IcpbParams()
+    lib().icpb_default_params(ctypes.byref(p))
+    return p

@@ -1,0 +1,382 @@
+// C ABI of the batched ICP library (include/icpb.h).  Plain CUDA runtime: no torch types, no
+// C++ exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include <vector>
+
+#include "icpb.h"
+#include "icpb_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            snprintf(g_err, sizeof g_err, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            return (int)e_;                                                               \
+        }                                                                                 \
+    } while (0)
+
+constexpr int kPointsPerThread = 4;
+constexpr int kQueueRing = 64;
+constexpr int kMaxSmem = 227 * 1024;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return (int)e; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct LaunchCfg {
+    int threads, smem, n2pad_cap, n1_cap, ctas_per_sm;
+};
+
+}  // namespace
+
+struct icpb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    // scan table
+    const double *xy = nullptr;
+    const int64_t *offsets = nullptr;
+    int64_t n_scans = 0, longest = 0;
+    DevBuf own_xy, own_off;
+    // queue counters
+    unsigned long long *queue = nullptr;
+    int64_t launches = 0;
+    // scratch for host-pointer entry points
+    DevBuf s_pairs, s_init, s_T, s_err, s_passes, s_hist, s_corr, s_pair_xy, s_pair_off;
+    cudaStream_t stream = nullptr;
+    int max_smem_set = 0;
+};
+
+namespace {
+
+int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c)
+{
+    if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
+    const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
+    const int64_t n1c = (longest + 3) & ~int64_t(3);
+    const int64_t smem = 8 * n2pad + 4 * n1c + 8 * (icpb::kMaxWarps * icpb::kNumSums + 8);
+    if (smem > kMaxSmem) {
+        snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
+                 (long long)longest, (long long)smem, kMaxSmem);
+        return ICPB_ETOOLONG;
+    }
+    int threads = (int)((longest + kPointsPerThread - 1) / kPointsPerThread);
+    threads = (threads + 31) / 32 * 32;
+    if (threads > 256) threads = 256;
+    if (threads < 32) threads = 32;
+    c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
+    if ((int)smem > h->max_smem_set) {
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->max_smem_set = (int)smem;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icpb::icp_align_kernel<kPointsPerThread>,
+                                                     threads, smem));
+    if (per_sm < 1) return fail(ICPB_EINVAL, "kernel does not fit on an SM%s");
+    c->ctas_per_sm = per_sm;
+    return 0;
+}
+
+int check_params(const icpb_params *p, int64_t B)
+{
+    if (!p) return fail(ICPB_EINVAL, "params is null%s");
+    if (B < 0) return fail(ICPB_EINVAL, "negative batch size%s");
+    if (p->hist_cap < 0 || p->corr_stride < 0) return fail(ICPB_EINVAL, "negative hist_cap/corr_stride%s");
+    if (p->pair_mode != 0 && p->pair_mode != 1) return fail(ICPB_EINVAL, "pair_mode must be 0 or 1%s");
+    if (p->pair_mode == 1 && p->k_block < 1) return fail(ICPB_EINVAL, "pair_mode 1 needs k_block >= 1%s");
+    if (isnan(p->epsilon) || isnan(p->stopping_thresh)) return fail(ICPB_EINVAL, "NaN epsilon/stopping_thresh%s");
+    return 0;
+}
+
+int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scans, int64_t longest,
+           const int32_t *d_pairs, const double *d_init, int64_t B, const icpb_params *p,
+           double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
+           cudaStream_t stream)
+{
+    if (B == 0) return 0;
+    LaunchCfg cfg;
+    int rc = make_cfg(h, longest, &cfg);
+    if (rc) return rc;
+    icpb::KernelArgs a;
+    a.xy = xy; a.offsets = offsets; a.pairs = d_pairs; a.init = d_init; a.B = B; a.n_scans = n_scans;
+    a.p = *p;
+    a.T_out = d_T; a.err_out = d_err; a.passes_out = d_passes;
+    a.hist = p->hist_cap > 0 ? d_hist : nullptr;
+    a.corr = p->corr_stride > 0 ? d_corr : nullptr;
+    a.queue = h->queue + (h->launches % kQueueRing);
+    a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap;
+    CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
+    int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
+    if (grid > B) grid = B;
+    icpb::icp_align_kernel<kPointsPerThread><<<(unsigned)grid, cfg.threads, cfg.smem, stream>>>(a);
+    CU(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void icpb_default_params(icpb_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->epsilon = 0.01;
+    p->stopping_thresh = 0.0001;
+    p->max_iters = 100;
+    p->k_block = 1;
+}
+
+int icpb_abi_version(void) { return ICPB_ABI_VERSION; }
+
+const char *icpb_last_error(void) { return g_err; }
+
+int icpb_create(int device, icpb_handle *out)
+{
+    if (!out) return fail(ICPB_EINVAL, "out is null%s");
+    *out = nullptr;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(ICPB_EINVAL, "no such CUDA device%s");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library is built for sm_100a only",
+                 device, prop.major, prop.minor);
+        return ICPB_EINVAL;
+    }
+    icpb_ctx *h = new (std::nothrow) icpb_ctx();
+    if (!h) return fail(ICPB_EINVAL, "out of host memory%s");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaMalloc(&h->queue, sizeof(unsigned long long) * kQueueRing);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "icpb_create: %s", cudaGetErrorString(e));
+        if (h->queue) cudaFree(h->queue);
+        delete h;
+        return (int)e;
+    }
+    *out = h;
+    return 0;
+}
+
+int icpb_destroy(icpb_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->own_xy.release(); h->own_off.release();
+    h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
+    h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
+    h->s_pair_xy.release(); h->s_pair_off.release();
+    if (h->queue) cudaFree(h->queue);
+    delete h;
+    return 0;
+}
+
+static int validate_offsets(const int64_t *off, int64_t n_scans, int64_t *longest)
+{
+    if (off[0] != 0) return fail(ICPB_EINVAL, "offsets[0] must be 0%s");
+    int64_t L = 0;
+    for (int64_t s = 0; s < n_scans; ++s) {
+        const int64_t m = off[s + 1] - off[s];
+        if (m <= 0) return fail(ICPB_EINVAL, "empty scan in the table (the reference's argmin raises on it)%s");
+        if (m > L) L = m;
+    }
+    *longest = L;
+    return 0;
+}
+
+int icpb_upload_scans(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans)
+{
+    if (!h || !h_xy || !h_offsets || n_scans <= 0) return fail(ICPB_EINVAL, "icpb_upload_scans: bad argument%s");
+    int64_t longest = 0;
+    int rc = validate_offsets(h_offsets, n_scans, &longest);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    const size_t nb_xy = sizeof(double) * 2 * (size_t)h_offsets[n_scans];
+    const size_t nb_off = sizeof(int64_t) * (size_t)(n_scans + 1);
+    if ((rc = h->own_xy.reserve(nb_xy))) return rc;
+    if ((rc = h->own_off.reserve(nb_off))) return rc;
+    CU(cudaMemcpyAsync(h->own_xy.p, h_xy, nb_xy, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->xy = (const double *)h->own_xy.p;
+    h->offsets = (const int64_t *)h->own_off.p;
+    h->n_scans = n_scans;
+    h->longest = longest;
+    return 0;
+}
+
+int icpb_set_scans_device(icpb_handle h, const double *d_xy, const int64_t *d_offsets,
+                          int64_t n_scans, int64_t longest_scan)
+{
+    if (!h || !d_xy || !d_offsets || n_scans <= 0 || longest_scan <= 0)
+        return fail(ICPB_EINVAL, "icpb_set_scans_device: bad argument%s");
+    h->xy = d_xy; h->offsets = d_offsets; h->n_scans = n_scans; h->longest = longest_scan;
+    return 0;
+}
+
+int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
+                    const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
+                    double *d_hist, int32_t *d_corr, void *stream)
+{
+    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
+    if (B > 0 && (!d_T || !d_err || !d_passes)) return fail(ICPB_EINVAL, "output pointer is null%s");
+    if (B > 0 && p->pair_mode == 0 && !d_pairs) return fail(ICPB_EINVAL, "pairs is null with pair_mode 0%s");
+    if (p->hist_cap > 0 && !d_hist) return fail(ICPB_EINVAL, "hist_cap > 0 but hist is null%s");
+    if (p->corr_stride > 0 && !d_corr) return fail(ICPB_EINVAL, "corr_stride > 0 but corr is null%s");
+    if (p->corr_stride > 0 && p->corr_stride < h->longest)
+        return fail(ICPB_EINVAL, "corr_stride is smaller than the longest scan%s");
+    CU(cudaSetDevice(h->device));
+    return launch(h, h->xy, h->offsets, h->n_scans, h->longest, d_pairs, d_init, B, p,
+                  d_T, d_err, d_passes, d_hist, d_corr, (cudaStream_t)stream);
+}
+
+static int run_host_common(icpb_handle h, const double *xy, const int64_t *offsets, int64_t n_scans,
+                           int64_t longest, const int32_t *h_pairs, const double *h_init, int64_t B,
+                           const icpb_params *p, double *h_T, double *h_err, int32_t *h_passes,
+                           double *h_hist, int32_t *h_corr)
+{
+    int rc;
+    cudaStream_t st = h->stream;
+    const size_t nbP = sizeof(int32_t) * 2 * (size_t)B, nbI = sizeof(double) * 6 * (size_t)B;
+    const size_t nbH = sizeof(double) * 6 * (size_t)B * (size_t)p->hist_cap;
+    const size_t nbC = sizeof(int32_t) * (size_t)B * (size_t)p->corr_stride;
+    if (p->pair_mode == 0) {
+        if ((rc = h->s_pairs.reserve(nbP))) return rc;
+        CU(cudaMemcpyAsync(h->s_pairs.p, h_pairs, nbP, cudaMemcpyHostToDevice, st));
+    }
+    if (h_init) {
+        if ((rc = h->s_init.reserve(nbI))) return rc;
+        CU(cudaMemcpyAsync(h->s_init.p, h_init, nbI, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = h->s_T.reserve(nbI))) return rc;
+    if ((rc = h->s_err.reserve(sizeof(double) * (size_t)B))) return rc;
+    if ((rc = h->s_passes.reserve(sizeof(int32_t) * (size_t)B))) return rc;
+    if (nbH) { if ((rc = h->s_hist.reserve(nbH))) return rc; CU(cudaMemsetAsync(h->s_hist.p, 0, nbH, st)); }
+    if (nbC) { if ((rc = h->s_corr.reserve(nbC))) return rc; CU(cudaMemsetAsync(h->s_corr.p, 0xff, nbC, st)); }
+    rc = launch(h, xy, offsets, n_scans, longest,
+                p->pair_mode == 0 ? (const int32_t *)h->s_pairs.p : nullptr,
+                h_init ? (const double *)h->s_init.p : nullptr, B, p,
+                (double *)h->s_T.p, (double *)h->s_err.p, (int32_t *)h->s_passes.p,
+                (double *)h->s_hist.p, (int32_t *)h->s_corr.p, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_T, h->s_T.p, nbI, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_err, h->s_err.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_passes, h->s_passes.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (nbH) CU(cudaMemcpyAsync(h_hist, h->s_hist.p, nbH, cudaMemcpyDeviceToHost, st));
+    if (nbC) CU(cudaMemcpyAsync(h_corr, h->s_corr.p, nbC, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, int64_t B,
+                  const icpb_params *p, double *h_T, double *h_err, int32_t *h_passes,
+                  double *h_hist, int32_t *h_corr)
+{
+    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
+    if (B == 0) return 0;
+    if (!h_T || !h_err || !h_passes) return fail(ICPB_EINVAL, "output pointer is null%s");
+    if (p->pair_mode == 0 && !h_pairs) return fail(ICPB_EINVAL, "pairs is null with pair_mode 0%s");
+    if (p->hist_cap > 0 && !h_hist) return fail(ICPB_EINVAL, "hist_cap > 0 but hist is null%s");
+    if (p->corr_stride > 0 && !h_corr) return fail(ICPB_EINVAL, "corr_stride > 0 but corr is null%s");
+    if (p->corr_stride > 0 && p->corr_stride < h->longest)
+        return fail(ICPB_EINVAL, "corr_stride is smaller than the longest scan%s");
+    if (p->pair_mode == 0) {
+        for (int64_t b = 0; b < 2 * B; ++b)
+            if (h_pairs[b] < 0 || h_pairs[b] >= h->n_scans) return fail(ICPB_EINVAL, "pair index out of range%s");
+    }
+    CU(cudaSetDevice(h->device));
+    return run_host_common(h, h->xy, h->offsets, h->n_scans, h->longest, h_pairs, h_init, B, p,
+                           h_T, h_err, h_passes, h_hist, h_corr);
+}
+
+int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,
+                       const double *h_dst_xy, int64_t n_dst, const double *h_init6,
+                       const icpb_params *p, double *h_T6, double *h_err, int32_t *h_passes,
+                       double *h_hist, int32_t *h_corr)
+{
+    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
+    if (!h_src_xy || !h_dst_xy || n_src <= 0 || n_dst <= 0)
+        return fail(ICPB_EINVAL, "empty point cloud (the reference's argmin raises on it)%s");
+    int rc = check_params(p, 1);
+    if (rc) return rc;
+    if (!h_T6 || !h_err || !h_passes) return fail(ICPB_EINVAL, "output pointer is null%s");
+    if (p->hist_cap > 0 && !h_hist) return fail(ICPB_EINVAL, "hist_cap > 0 but hist is null%s");
+    if (p->corr_stride > 0 && (!h_corr || p->corr_stride < n_src))
+        return fail(ICPB_EINVAL, "corr buffer missing or shorter than the source cloud%s");
+    icpb_params q = *p;
+    q.pair_mode = 0; q.k_first = 0; q.k_block = 1; q.k_stride = 0;
+    CU(cudaSetDevice(h->device));
+    const size_t nb = sizeof(double) * 2 * (size_t)(n_src + n_dst);
+    if ((rc = h->s_pair_xy.reserve(nb))) return rc;
+    if ((rc = h->s_pair_off.reserve(sizeof(int64_t) * 3))) return rc;
+    const int64_t off[3] = {0, n_src, n_src + n_dst};
+    const int32_t pair[2] = {0, 1};
+    double *dxy = (double *)h->s_pair_xy.p;
+    CU(cudaMemcpyAsync(dxy, h_src_xy, sizeof(double) * 2 * (size_t)n_src, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dxy + 2 * n_src, h_dst_xy, sizeof(double) * 2 * (size_t)n_dst, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->s_pair_off.p, off, sizeof off, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));       // `off` lives on this stack frame
+    return run_host_common(h, dxy, (const int64_t *)h->s_pair_off.p, 2, n_src > n_dst ? n_src : n_dst,
+                           pair, h_init6, 1, &q, h_T6, h_err, h_passes, h_hist, h_corr);
+}
+
+int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out)
+{
+    if (!h || !out) return fail(ICPB_EINVAL, "icpb_get_kernel_info: bad argument%s");
+    if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
+    CU(cudaSetDevice(h->device));
+    LaunchCfg cfg;
+    int rc = make_cfg(h, h->longest, &cfg);
+    if (rc) return rc;
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, icpb::icp_align_kernel<kPointsPerThread>));
+    int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
+    if (B > 0 && grid > B) grid = B;
+    out->threads_per_cta = cfg.threads; out->ctas_per_sm = cfg.ctas_per_sm; out->sm_count = h->sm_count;
+    out->grid = (int32_t)grid; out->regs_per_thread = fa.numRegs; out->smem_bytes = cfg.smem;
+    out->points_per_thread = kPointsPerThread; out->variant = 1;
+    return 0;
+}
+
+int64_t icpb_launch_count(icpb_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

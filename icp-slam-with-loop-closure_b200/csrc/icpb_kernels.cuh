@@ -1,0 +1,371 @@
+// Batched 2-D point-to-point ICP for sm_100a: one CTA per scan pair, the whole
+// iterate-until-converged loop of the reference's icp() (reference src/icp.py:72-97) in-kernel.
+//
+// Numerical contract (DESIGN.md "Exactness"):
+//   * the O(N1*N2) nearest-neighbour sweep runs in fp32 and only *filters*: per source point it
+//     yields the best 16-target chunk, the best fp32 distance m1 and the best fp32 distance m2
+//     found in any other chunk;
+//   * every target whose fp32 distance is within a rigorous rounding bound of m1 is then
+//     re-evaluated in fp64 with the reference's own arithmetic ((dx*dx)+(dy*dy), separately
+//     rounded, src/icp.py:6) and the winner is the lexicographic (distance, index) minimum,
+//     i.e. np.argmin's first-index rule (src/icp.py:7).  If another chunk is within the bound
+//     (m2 <= m1 + tol) the whole target is re-filtered.  So the correspondences are those of an
+//     all-fp64 search, and fp32 only decides how much fp64 work is needed;
+//   * transform application, centroids, cross-covariance, error, composition and the stop
+//     rules are fp64, reduced in a fixed order (deterministic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "icpb.h"
+
+namespace icpb {
+
+constexpr int   kChunk    = 16;        // targets per bookkeeping chunk
+constexpr float kPadCoord = 1.0e15f;   // coordinates of padding targets (distance ~2e30, never a candidate)
+constexpr int   kMaxWarps = 32;
+constexpr int   kNumSums  = 9;
+
+struct KernelArgs {
+    const double  *xy;        // scan table, (sum m_i, 2) fp64
+    const int64_t *offsets;   // CSR offsets, n_scans + 1
+    const int32_t *pairs;     // B x 2 or nullptr (pair_mode 1)
+    const double  *init;      // B x 6 or nullptr
+    int64_t        B;
+    int64_t        n_scans;
+    icpb_params    p;
+    double        *T_out;     // B x 6
+    double        *err_out;   // B
+    int32_t       *passes_out;// B
+    double        *hist;      // B x hist_cap x 6 or nullptr
+    int32_t       *corr;      // B x corr_stride or nullptr
+    unsigned long long *queue;// work-queue counter (zeroed before launch)
+    int32_t        n2pad_cap; // floats per target coordinate array in shared memory
+    int32_t        n1_cap;    // int32 slots for correspondences in shared memory
+};
+
+// ---- fp32 filter distance: one definition, used by the sweep and by the refine step ----------
+__device__ __forceinline__ float dist32(float px, float py, float qx, float qy)
+{
+    const float dx = __fsub_rn(qx, px);
+    const float dy = __fsub_rn(qy, py);
+    return __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+}
+
+// ---- fp64 distance with the reference's rounding: (dx*dx) + (dy*dy), no contraction ----------
+__device__ __forceinline__ double dist64(double px, double py, double qx, double qy)
+{
+    const double dx = __dsub_rn(qx, px);
+    const double dy = __dsub_rn(qy, py);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// p' = T p, accumulated in the order a k-loop over the three homogeneous columns does
+// (src/icp.py:62: np.dot(previous_transform, pc1.T).T).
+__device__ __forceinline__ void apply_T(const double *T, double x, double y, double &ox, double &oy)
+{
+    ox = fma(T[1], y, T[0] * x) + T[2];
+    oy = fma(T[4], y, T[3] * x) + T[5];
+}
+
+__device__ __forceinline__ float min3f(float a, float b, float c)
+{
+    return fminf(fminf(a, b), c);
+}
+
+// Bound on |fp32 filter distance - exact distance| doubled, as a function of the best filter
+// distance m1.  e bounds the error of one coordinate difference: both inputs were rounded to
+// fp32 (relative 2^-24 each) and the subtraction rounds once more.
+__device__ __forceinline__ float filter_tol(float m1, float px, float py, float qmax)
+{
+    const float u = 5.9604645e-8f;                              // 2^-24
+    const float e = 2.0f * u * (fmaxf(fabsf(px), fabsf(py)) + qmax) * 1.0001f;
+    return 8.0f * sqrtf(m1) * e + 16.0f * e * e + 16.0f * u * m1;
+}
+
+// All targets j in [lo, hi) whose filter distance is <= thr are evaluated exactly; keeps the
+// lexicographic (distance, index) minimum.  j ascends, so strict < keeps the first index.
+__device__ __forceinline__ void refine_range(int lo, int hi, float thr, float px, float py,
+                                             double Px, double Py, const float *tqx, const float *tqy,
+                                             const double2 *dst, double &best, int &idx)
+{
+    for (int j = lo; j < hi; ++j) {
+        const float d = dist32(px, py, tqx[j], tqy[j]);
+        if (d <= thr) {
+            const double2 q = dst[j];
+            const double D = dist64(Px, Py, q.x, q.y);
+            if (D < best) { best = D; idx = j; }
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// linear index over the strict upper triangle of an n x n matrix, row-major -> (i, j), i < j
+__device__ __forceinline__ void decode_pair(int64_t k, int64_t n, int32_t &i_out, int32_t &j_out)
+{
+    const double nn = (double)n - 0.5;
+    int64_t i = (int64_t)(nn - sqrt(nn * nn - 2.0 * (double)k));
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    while (i > 0 && i * (2 * n - i - 1) / 2 > k) --i;
+    while ((i + 1) * (2 * n - i - 2) / 2 <= k) ++i;
+    const int64_t start = i * (2 * n - i - 1) / 2;
+    i_out = (int32_t)i;
+    j_out = (int32_t)(k - start + i + 1);
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+icp_align_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float  *tqx    = reinterpret_cast<float *>(smem_raw);
+    float  *tqy    = tqx + a.n2pad_cap;
+    int    *corr_s = reinterpret_cast<int *>(tqy + a.n2pad_cap);
+    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // 16B aligned
+    double *ctl    = red + kMaxWarps * kNumSums;     // [0..5] T, [6] err, [7] done flag
+    __shared__ long long s_pid;
+    __shared__ unsigned int s_qmax_bits;
+
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+
+    for (;;) {
+        // ---------------- pop a problem ----------------
+        if (tid == 0) {
+            s_pid = (long long)atomicAdd(a.queue, 1ULL);
+            s_qmax_bits = 0u;
+        }
+        __syncthreads();
+        const int64_t pid = s_pid;
+        if (pid >= a.B) return;
+
+        int32_t sid, did;
+        if (a.p.pair_mode == 1) {
+            const int64_t k = a.p.k_first + (pid / a.p.k_block) * a.p.k_stride + (pid % a.p.k_block);
+            int32_t i, j;
+            decode_pair(k, a.n_scans, i, j);
+            sid = j; did = i;
+        } else {
+            sid = a.pairs[2 * pid]; did = a.pairs[2 * pid + 1];
+        }
+        const int64_t so = a.offsets[sid], dof = a.offsets[did];
+        const int n1 = (int)(a.offsets[sid + 1] - so);
+        const int n2 = (int)(a.offsets[did + 1] - dof);
+        const double2 *src = reinterpret_cast<const double2 *>(a.xy) + so;
+        const double2 *dst = reinterpret_cast<const double2 *>(a.xy) + dof;
+        const int n2pad = (n2 + kChunk - 1) / kChunk * kChunk;
+        const int nchunks = n2pad / kChunk;
+
+        // ---------------- stage the target in shared memory as fp32 SoA ----------------
+        {
+            float qm = 0.0f;
+            for (int j = tid; j < n2pad; j += NT) {
+                float x = kPadCoord, y = kPadCoord;
+                if (j < n2) {
+                    const double2 q = dst[j];
+                    x = (float)q.x; y = (float)q.y;
+                    qm = fmaxf(qm, fmaxf(fabsf(x), fabsf(y)));
+                }
+                tqx[j] = x; tqy[j] = y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, o));
+            if (lane == 0) atomicMax(&s_qmax_bits, __float_as_uint(qm));   // qm >= 0: bit order = value order
+        }
+        if (tid < 6) {
+            double v = a.init ? a.init[6 * pid + tid] : ((tid == 0 || tid == 4) ? 1.0 : 0.0);
+            if (a.p.rotation_only && (tid == 2 || tid == 5)) v = 0.0;       // src/icp.py:60-61
+            ctl[tid] = v;
+        }
+        __syncthreads();
+        const float qmax = __uint_as_float(s_qmax_bits);
+        const double2 g = dst[0];                 // shift for the one-pass covariance sums
+
+        int passes = 0, iteration = 0;
+        bool have_last = false;
+        double last_err = 0.0;
+
+        for (;;) {
+            double T[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) T[k] = ctl[k];
+
+            // =========== P1: nearest neighbours (src/icp.py:10-19) ===========
+            for (int base = 0; base < n1; base += NT * R) {
+                if (base + warp * 32 * R >= n1) break;          // this warp has no points in the tile
+                const int i0 = base + tid * R;
+                float px[R], py[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = min(i0 + r, n1 - 1);
+                    const double2 s = src[i];
+                    double X, Y;
+                    apply_T(T, s.x, s.y, X, Y);
+                    px[r] = (float)X; py[r] = (float)Y;
+                }
+                float m1[R], m2[R];
+                int c1[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { m1[r] = __int_as_float(0x7f800000); m2[r] = m1[r]; c1[r] = 0; }
+
+                const float4 *qx4 = reinterpret_cast<const float4 *>(tqx);
+                const float4 *qy4 = reinterpret_cast<const float4 *>(tqy);
+#pragma unroll 1
+                for (int c = 0; c < nchunks; ++c) {
+                    float4 X[4], Y[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float d[16];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            d[4 * v + 0] = dist32(px[r], py[r], X[v].x, Y[v].x);
+                            d[4 * v + 1] = dist32(px[r], py[r], X[v].y, Y[v].y);
+                            d[4 * v + 2] = dist32(px[r], py[r], X[v].z, Y[v].z);
+                            d[4 * v + 3] = dist32(px[r], py[r], X[v].w, Y[v].w);
+                        }
+                        float cm = min3f(d[0], d[1], d[2]);
+                        cm = min3f(cm, d[3], d[4]);
+                        cm = min3f(cm, d[5], d[6]);
+                        cm = min3f(cm, d[7], d[8]);
+                        cm = min3f(cm, d[9], d[10]);
+                        cm = min3f(cm, d[11], d[12]);
+                        cm = min3f(cm, d[13], d[14]);
+                        cm = fminf(cm, d[15]);
+                        const bool better = cm < m1[r];
+                        m2[r] = fminf(m2[r], better ? m1[r] : cm);
+                        m1[r] = fminf(m1[r], cm);
+                        c1[r] = better ? c : c1[r];
+                    }
+                }
+                // ---- refine: exact fp64 decision among the filter's candidates ----
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = i0 + r;
+                    if (i < n1) {
+                        const double2 s = src[i];
+                        double Px, Py;
+                        apply_T(T, s.x, s.y, Px, Py);
+                        const float thr = m1[r] + filter_tol(m1[r], px[r], py[r], qmax);
+                        double best = __longlong_as_double(0x7ff0000000000000LL);
+                        int idx = c1[r] * kChunk < n2 ? c1[r] * kChunk : 0;
+                        if (m2[r] <= thr)
+                            refine_range(0, n2, thr, px[r], py[r], Px, Py, tqx, tqy, dst, best, idx);
+                        else
+                            refine_range(c1[r] * kChunk, min(c1[r] * kChunk + kChunk, n2), thr, px[r], py[r],
+                                         Px, Py, tqx, tqy, dst, best, idx);
+                        corr_s[i] = idx;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // =========== P2: sums for the rigid fit and the error (src/icp.py:22-52) ===========
+            double cx, cy;                                   // shift = transformed first source point
+            {
+                const double2 s0 = src[0];
+                apply_T(T, s0.x, s0.y, cx, cy);
+            }
+            double sum[kNumSums];
+#pragma unroll
+            for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+            for (int i = tid; i < n1; i += NT) {
+                const double2 s = src[i];
+                double Px, Py;
+                apply_T(T, s.x, s.y, Px, Py);
+                const double2 q = dst[corr_s[i]];
+                const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
+                sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
+                sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
+                sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
+                const double ex = Px - q.x, ey = Py - q.y;
+                sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+            }
+#pragma unroll
+            for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kNumSums; ++k) red[warp * kNumSums + k] = sum[k];
+            }
+            __syncthreads();
+
+            if (warp == 0) {
+                // fixed-order cross-warp sum: lane k (< 9) adds column k over the warps in order
+                double tot = 0.0;
+                if (lane < kNumSums)
+                    for (int w = 0; w < nwarps; ++w) tot += red[w * kNumSums + lane];
+                double S[kNumSums];
+#pragma unroll
+                for (int k = 0; k < kNumSums; ++k) S[k] = __shfl_sync(0xffffffffu, tot, k);
+                if (lane == 0) {
+                    const double n = (double)n1;
+                    const double ma_x = S[0] / n, ma_y = S[1] / n, mb_x = S[2] / n, mb_y = S[3] / n;
+                    // centred cross-covariance S = X Y^T (src/icp.py:29-32)
+                    const double s00 = S[4] - S[0] * mb_x, s01 = S[5] - S[0] * mb_y;
+                    const double s10 = S[6] - S[1] * mb_x, s11 = S[7] - S[1] * mb_y;
+                    // rotation maximising tr(R S): closed form of the SVD + det fix (src/icp.py:33-38)
+                    const double A = s00 + s11, Bv = s01 - s10;
+                    const double h = hypot(A, Bv);
+                    double c = 1.0, s = 0.0;
+                    if (h > 0.0) { c = A / h; s = Bv / h; }
+                    const double xbar = cx + ma_x, ybar = cy + ma_y;       // mean of moved source
+                    const double qbx = g.x + mb_x, qby = g.y + mb_y;       // mean of matched target
+                    double tx = qbx - (c * xbar - s * ybar);               // src/icp.py:39
+                    double ty = qby - (s * xbar + c * ybar);
+                    if (a.p.rotation_only) { tx = 0.0; ty = 0.0; }         // src/icp.py:65-66
+                    double N[6];                                           // inc @ T (src/icp.py:67)
+                    N[0] = c * T[0] - s * T[3];
+                    N[1] = c * T[1] - s * T[4];
+                    N[2] = c * T[2] - s * T[5] + tx;
+                    N[3] = s * T[0] + c * T[3];
+                    N[4] = s * T[1] + c * T[4];
+                    N[5] = s * T[2] + c * T[5] + ty;
+                    const double err = S[8];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) ctl[k] = N[k];
+                    ctl[6] = err;
+                    if (a.hist && passes < a.p.hist_cap) {
+                        double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) hrow[k] = N[k];
+                    }
+                    // stop rules, in the reference's order (src/icp.py:86-95)
+                    bool done = err < a.p.epsilon;
+                    if (!done) done = iteration > a.p.max_iters;
+                    if (!done && have_last) done = fabs(last_err - err) < a.p.stopping_thresh;
+                    ctl[7] = done ? 1.0 : 0.0;
+                }
+            }
+            __syncthreads();
+            ++passes;
+            const double err = ctl[6];
+            const bool done = ctl[7] != 0.0;
+            if (done) {
+                if (tid == 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = ctl[k];
+                    a.err_out[pid] = err;
+                    a.passes_out[pid] = passes;
+                }
+                if (a.corr) {
+                    int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;
+                    const int lim = min(n1, a.p.corr_stride);
+                    for (int i = tid; i < lim; i += NT) crow[i] = corr_s[i];
+                }
+                break;
+            }
+            last_err = err; have_last = true;
+            ++iteration;
+        }
+        __syncthreads();        // smem is reused by the next problem
+    }
+}
+
+}  // namespace icpb

@@ -1,0 +1,126 @@
+/*
+ * icpb -- batched 2-D point-to-point ICP scan matching on B200 (sm_100a): C ABI.
+ *
+ * This is the drop-in boundary for the reference's ICP path.  The reference has no FFI: the
+ * path is the module-level Python functions of src/icp.py, fanned out over scan pairs by
+ * joblib.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a non-zero status otherwise (a cudaError_t value,
+ *     or one of the ICPB_E* codes); nothing throws across the ABI; icpb_last_error() returns
+ *     a per-thread message for the last failure.
+ *   - scans are (m_i, 2) float64 rows in one concatenated table with int64 CSR offsets -- the
+ *     arrays the reference's dataloader returns (src/dataloader.py:47-55,110-112), before the
+ *     callers append the homogeneous column of ones (scripts/main.py:242-243).
+ *   - a transform is the top 2x3 of the reference's 3x3 SE(2) matrix, row-major, float64:
+ *     [r00 r01 tx r10 r11 ty]; the bottom row is always [0 0 1] (src/icp.py:41-44,67).
+ *   - pairs[b] = (source scan id, target scan id): the source is moved onto the target, the
+ *     reference's icp(pc1=source, pc2=target) (src/icp.py:72-76).
+ *   - pointers named d_* are device pointers on the handle's device, h_* host pointers.
+ */
+#ifndef ICPB_H
+#define ICPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICPB_ABI_VERSION 1
+
+#define ICPB_EINVAL   10001   /* bad argument (null pointer, empty scan, negative size ...)   */
+#define ICPB_ETOOLONG 10002   /* a scan does not fit the kernel's shared-memory staging       */
+#define ICPB_ENOSCANS 10003   /* run called before a scan table was set                       */
+
+typedef struct icpb_ctx *icpb_handle;
+
+/* Keyword arguments of the reference's icp() (src/icp.py:72) plus batch bookkeeping. */
+typedef struct icpb_params {
+    double  epsilon;          /* stop when error < epsilon               (src/icp.py:86)      */
+    double  stopping_thresh;  /* stop when |last_err - err| < this       (src/icp.py:91-95)   */
+    int32_t max_iters;        /* stop when iteration > max_iters: up to max_iters+2 passes (:88) */
+    int32_t rotation_only;    /* zero the translation every pass         (src/icp.py:60-61,65-66) */
+    int32_t hist_cap;         /* transforms recorded per problem in hist (0 = none)           */
+    int32_t corr_stride;      /* int32 slots per problem in corr (0 = none); >= longest source */
+    int32_t pair_mode;        /* 0: explicit pairs array; 1: all pairs i<j of n_scans, source=j,
+                                 target=i (the argument order of src/loop_closure_detection.py:31-34),
+                                 decoded on the device from a linear index                    */
+    int32_t reserved;
+    /* pair_mode 1 and sharding: problem b of this call is global index
+       k = k_first + (b / k_block) * k_stride + (b % k_block); with pair_mode 0 and pairs given
+       for this shard only, leave k_first = 0, k_block = B, k_stride = 0.                      */
+    int64_t k_first, k_block, k_stride;
+} icpb_params;
+
+/* Fills the reference's icp() defaults: epsilon 0.01, max_iters 100, stopping_thresh 1e-4,
+ * rotation_only 0 (src/icp.py:72); no history, no correspondences, explicit pairs. */
+void icpb_default_params(icpb_params *p);
+
+int icpb_abi_version(void);
+
+/* Per-process, per-device state: the staged scan table, the work-queue counter, scratch
+ * buffers for the host-pointer entry point.  Replaces "a loky worker process"
+ * (scripts/main.py:240, src/loop_closure_detection.py:134). */
+int icpb_create(int device, icpb_handle *out);
+int icpb_destroy(icpb_handle h);
+
+/* Scan table = the reference's `lidar_points` list (src/dataloader.py:110-112), concatenated.
+ * icpb_upload_scans copies host arrays into device memory owned by the handle;
+ * icpb_set_scans_device borrows device arrays the caller keeps alive.  offsets has
+ * n_scans + 1 entries, offsets[0] = 0. */
+int icpb_upload_scans(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans);
+int icpb_set_scans_device(icpb_handle h, const double *d_xy, const int64_t *d_offsets,
+                          int64_t n_scans, int64_t longest_scan);
+
+/*
+ * B independent icp() calls (src/icp.py:72-97) in one launch -- replaces the joblib fan-out
+ * `Parallel(...)(delayed(icp.icp)(...) for ...)` of scripts/main.py:240-247,
+ * src/loop_closure_detection.py:134-142 and src/pose_graph_optimization.py:60-68.
+ *   d_pairs   B x 2 int32 (pair_mode 0) or NULL (pair_mode 1)
+ *   d_init    B x 6 float64 initial transforms (icp()'s init_transform) or NULL for identity
+ *   d_T       B x 6 float64   transforms[-1] of each call
+ *   d_err     B     float64   the returned error (SSE under transforms[-2], src/icp.py:68)
+ *   d_passes  B     int32     len(transforms) - 1
+ *   d_hist    B x hist_cap x 6 float64 or NULL: transforms[1:], rows past the pass count untouched
+ *   d_corr    B x corr_stride int32 or NULL: the last pass's correspondences (icp_iteration's
+ *             second return value, src/icp.py:63,69)
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ */
+int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
+                    const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
+                    double *d_hist, int32_t *d_corr, void *stream);
+
+/* Same with host buffers: copies the inputs to the device, runs, copies the results back and
+ * synchronises.  This is the call a reference-side binding makes. */
+int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, int64_t B,
+                  const icpb_params *p, double *h_T, double *h_err, int32_t *h_passes,
+                  double *h_hist, int32_t *h_corr);
+
+/* One pair given directly as two (n, 2) float64 host arrays: the reference's
+ * icp(pc1, pc2, init_transform, epsilon, max_iters, stopping_thresh, rotation_only)
+ * (src/icp.py:72) and, with epsilon = +inf (one pass), icp_iteration() (src/icp.py:55-69). */
+int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,
+                       const double *h_dst_xy, int64_t n_dst, const double *h_init6,
+                       const icpb_params *p, double *h_T6, double *h_err, int32_t *h_passes,
+                       double *h_hist, int32_t *h_corr);
+
+/* Launch geometry and resource use of the alignment kernel for the current scan table
+ * (reported by bench.py next to the roofline numbers). */
+typedef struct icpb_kernel_info {
+    int32_t threads_per_cta, ctas_per_sm, sm_count, grid;
+    int32_t regs_per_thread, smem_bytes, points_per_thread, variant;
+} icpb_kernel_info;
+int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out);
+
+/* Number of alignment-kernel launches made through this handle (bench.py's gpu_launches). */
+int64_t icpb_launch_count(icpb_handle h);
+
+const char *icpb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICPB_H */

@@ -1,0 +1,245 @@
+"""Parity of the CUDA path (through the C ABI in libicpb.so) against the oracle and the golden
+outputs of the unmodified reference.  Tolerances (BASELINE.json north_star): correspondence
+indices bit-exact (ties aside), final poses within 1e-5 m / 1e-5 rad at a matched pass count.
+The tests hold the kernel to far tighter bounds: 1e-9 on every transform of the history.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, pose_diff
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_golden()
+IDS = [c.name for c in CASES]
+POSE_TOL = 1e-9          # metres / radians; the contract is 1e-5
+
+
+@pytest.fixture(scope="module")
+def gicp():
+    from icp_slam_b200 import icp as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def c_oracle():
+    from oracle import c_oracle as m
+    m.build()
+    return m
+
+
+def hom(s):
+    return np.c_[s, np.ones(len(s))]
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_icp_matches_reference_golden(gicp, case):
+    init = case.init.copy()
+    tfs, err = gicp.icp(hom(case.src), hom(case.dst), init, **case.kwargs)
+    assert isinstance(tfs, list) and tfs[0] is init
+    assert isinstance(err, np.float64)
+    assert len(tfs) == len(case.transforms)                       # matched pass count
+    dt, dth = pose_diff(np.stack(tfs), case.transforms)
+    assert dt < POSE_TOL and dth < POSE_TOL
+    np.testing.assert_allclose(np.stack(tfs), case.transforms, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(err, case.error, rtol=1e-9, atol=1e-20)
+    np.testing.assert_array_equal(init, case.init_after)          # in-place zeroing under rotation_only
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_icp_iteration_correspondences_bit_exact(gicp, case):
+    """Replay every pass from the reference's own starting transform: the correspondences must
+    be identical index for index (np.argmin first-index rule included)."""
+    for k in range(len(case.transforms) - 1):
+        start = case.transforms[k].copy()
+        T, corr, err = gicp.icp_iteration(hom(case.src), hom(case.dst), start,
+                                          rotation_only=bool(case.rotation_only))
+        assert corr.dtype == np.int64 and corr.shape == (len(case.src),)
+        np.testing.assert_array_equal(corr, case.correspondences[k])
+        np.testing.assert_allclose(T, case.transforms[k + 1], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(err, case.pass_errors[k], rtol=1e-9, atol=1e-20)
+
+
+@pytest.mark.parametrize("n_beams,n_scans", [(90, 40), (360, 64), (1024, 48)])
+def test_batch_chain_vs_oracle(gicp, c_oracle, n_beams, n_scans):
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(n_scans, n_beams, seed=467002 + n_beams)
+    res = gicp.icp_batch(scans, pairs, init, epsilon=0.05, max_iters=100,
+                         return_history=True, return_correspondences=True)
+    xy, off = c_oracle.pack(scans)
+    T, err, passes = c_oracle.icp_batch(xy, off, pairs, init, epsilon=0.05, max_iters=100)
+    np.testing.assert_array_equal(res.iters, passes)
+    dt, dth = pose_diff(res.T, T)
+    assert dt < POSE_TOL and dth < POSE_TOL
+    np.testing.assert_allclose(res.error, err, rtol=1e-9)
+    for b in range(0, len(pairs), 5):
+        s, d = pairs[b]
+        _, _, p1, corr, hist = c_oracle.icp_pair(scans[s], scans[d], init[b], epsilon=0.05, want_history=True)
+        np.testing.assert_array_equal(res.correspondences[b, :len(corr)], corr)
+        assert np.all(res.correspondences[b, len(corr):] == -1)
+        np.testing.assert_allclose(res.history[b, :p1], hist, rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(res.history[b, p1:], np.broadcast_to(np.eye(3), res.history[b, p1:].shape))
+
+
+def test_batch_loop_closure_pairs_identity_init(gicp, c_oracle):
+    """Proximity-like pairs, identity init, many passes, some hitting the 102-pass cap."""
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(467003)
+    poses = synth.loop_trajectory(60, step=0.35)
+    scans = synth.scans_from_poses(poses, 512, rng, drop_frac=0.03)
+    pairs = np.array([(j, i) for i in range(0, 60, 3) for j in (i + 1, i + 2, (i + 31) % 60)], dtype=np.int32)
+    res = gicp.icp_batch(scans, pairs, None, epsilon=0.05, max_iters=100)
+    xy, off = c_oracle.pack(scans)
+    T, err, passes = c_oracle.icp_batch(xy, off, pairs, None, epsilon=0.05, max_iters=100)
+    np.testing.assert_array_equal(res.iters, passes)
+    assert passes.max() > 40
+    dt, dth = pose_diff(res.T, T)
+    assert dt < POSE_TOL and dth < POSE_TOL
+    np.testing.assert_allclose(res.error, err, rtol=1e-9)
+
+
+def test_exact_ties_first_index(gicp, c_oracle):
+    """Integer-lattice clouds: many exactly equal distances.  The fp64 refine must reproduce
+    np.argmin's first-index rule, also across 16-target chunks and with duplicated targets."""
+    rng = np.random.default_rng(7)
+    gx, gy = np.meshgrid(np.arange(12.0), np.arange(9.0))
+    lattice = np.stack((gx.ravel(), gy.ravel()), axis=1)
+    dst = lattice[rng.permutation(len(lattice))]
+    dst = np.concatenate((dst, dst[:40]))                            # duplicates: ties at distance equality
+    src = lattice[rng.permutation(len(lattice))][:77] + 0.5          # equidistant to 4 lattice points
+    T, corr, err = gicp.icp_iteration(hom(src), hom(dst), np.eye(3))
+    _, e2, p2, corr2 = c_oracle.icp_pair(src, dst, epsilon=np.inf)
+    np.testing.assert_array_equal(corr, corr2)
+    assert abs(err - e2) <= 1e-12 * max(1.0, e2)
+    # brute force with numpy's own argmin
+    d = ((dst[None, :, :] - src[:, None, :]) ** 2).sum(-1)
+    np.testing.assert_array_equal(corr, np.argmin(d, axis=1))
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 5), (2, 3), (15, 17), (16, 16), (33, 31), (129, 257),
+                                   (1000, 1024), (1025, 999), (4096, 4096), (5000, 3000)])
+def test_ragged_sizes(gicp, c_oracle, n1, n2):
+    rng = np.random.default_rng(n1 * 7919 + n2)
+    dst = rng.uniform(-8, 8, size=(n2, 2))
+    th = 0.04
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    base = dst[rng.integers(0, n2, size=n1)] + rng.normal(0, 0.01, size=(n1, 2))
+    src = (base - np.array([0.05, -0.03])) @ R
+    res = gicp.icp_batch([src, dst], np.array([[0, 1]]), None, epsilon=1e-6, max_iters=20,
+                         return_correspondences=True)
+    T, err, passes, corr = c_oracle.icp_pair(src, dst, None, epsilon=1e-6, max_iters=20)
+    assert res.iters[0] == passes
+    np.testing.assert_array_equal(res.correspondences[0, :n1], corr)
+    if len(set(corr.tolist())) >= 2:             # one matched target: rotation is rounding noise in the reference too
+        dt, dth = pose_diff(res.T[0], T)
+        assert dt < POSE_TOL and dth < POSE_TOL
+    np.testing.assert_allclose(res.error[0], err, rtol=1e-9, atol=1e-20)
+
+
+def test_stop_rules_and_rotation_only(gicp, c_oracle):
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(10, 256, seed=5)
+    for kw in (dict(epsilon=0.0, stopping_thresh=0.0, max_iters=0), dict(epsilon=0.0, stopping_thresh=0.0, max_iters=7),
+               dict(epsilon=1e9), dict(epsilon=0.05, rotation_only=True), dict(stopping_thresh=10.0),
+               dict(epsilon=0.0, stopping_thresh=0.0, max_iters=-5)):
+        res = gicp.icp_batch(scans, pairs, init, **kw)
+        xy, off = c_oracle.pack(scans)
+        T, err, passes = c_oracle.icp_batch(xy, off, pairs, init, **kw)
+        np.testing.assert_array_equal(res.iters, passes)
+        if "max_iters" in kw and kw.get("epsilon") == 0.0:
+            assert np.all(passes == max(kw["max_iters"] + 2, 1))      # the reference's off-by-two cap
+        dt, dth = pose_diff(res.T, T)
+        assert dt < POSE_TOL and dth < POSE_TOL
+        if kw.get("rotation_only"):
+            assert np.all(res.T[:, :2, 2] == 0.0)
+
+
+def test_identical_clouds_stop_after_one_pass(gicp):
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-5, 5, size=(300, 2))
+    tfs, err = gicp.icp(hom(a), hom(a.copy()))
+    assert len(tfs) == 2 and err == 0.0
+    np.testing.assert_allclose(tfs[-1], np.eye(3), atol=1e-15)
+
+
+def test_fortran_ordered_and_positional_use(gicp, c_oracle):
+    """scripts/produce_loop_closure_icp_figure.py:18-21,31 passes transposed (F-ordered) views;
+    scripts/test_icp.py:54 calls icp(pc1, pc2) positionally with all defaults."""
+    rng = np.random.default_rng(9)
+    dst = rng.uniform(-4, 4, size=(150, 2))
+    src = dst[:120] + 0.02
+    pc1 = np.asfortranarray(hom(src))
+    pc2 = np.vstack((dst.T, np.ones(len(dst)))).T
+    tfs, err = gicp.icp(pc1, pc2)
+    T, e, passes, _ = c_oracle.icp_pair(src, dst)
+    assert len(tfs) - 1 == passes
+    np.testing.assert_allclose(tfs[-1], T, atol=1e-9)
+
+
+def test_all_pairs_device_decode(gicp, c_oracle):
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(12)
+    poses = synth.loop_trajectory(9, step=0.1)
+    scans = synth.scans_from_poses(poses, 128, rng)
+    e = gicp.engine()
+    e.set_scans(scans)
+    n = len(scans)
+    B = synth.all_pairs_count(n)
+    res = e.run(None, None, epsilon=0.05, max_iters=30, all_pairs=(0, B, 0, B))
+    ij = synth.all_pairs_decode(np.arange(B), n)
+    pairs = np.stack((ij[:, 1], ij[:, 0]), axis=1).astype(np.int32)        # source = j, target = i
+    ref = e.run(pairs, None, epsilon=0.05, max_iters=30)
+    np.testing.assert_array_equal(res.T, ref.T)
+    np.testing.assert_array_equal(res.iters, ref.iters)
+    # sharded: 2 ranks, blocks of 5, interleaved
+    got = {}
+    for rank in range(2):
+        ks = [k for k in range(B) if (k // 5) % 2 == rank]
+        r = e.run(None, None, epsilon=0.05, max_iters=30, all_pairs=(rank * 5, 5, 10, len(ks)))
+        for k, T in zip(ks, r.T):
+            got[k] = T
+    np.testing.assert_array_equal(np.stack([got[k] for k in range(B)]), ref.T)
+    xy, off = c_oracle.pack(scans)
+    T, err, passes = c_oracle.icp_batch(xy, off, pairs, None, epsilon=0.05, max_iters=30)
+    np.testing.assert_array_equal(ref.iters, passes)
+
+
+def test_device_buffer_entry_point(gicp):
+    import torch
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(20, 360, seed=77)
+    e = gicp.engine()
+    table = e.set_scans(scans)
+    ref = e.run(pairs, init, epsilon=0.05)
+    dev = torch.device("cuda", e.device)
+    xy_t = torch.from_numpy(table.xy).to(dev)
+    off_t = torch.from_numpy(table.offsets).to(dev)
+    e.set_scans_device(xy_t, off_t, table)
+    B = len(pairs)
+    pairs_t = torch.from_numpy(pairs).to(dev)
+    init_t = torch.from_numpy(np.ascontiguousarray(init[:, :2, :].reshape(B, 6))).to(dev)
+    oT = torch.empty((B, 6), dtype=torch.float64, device=dev)
+    oe = torch.empty(B, dtype=torch.float64, device=dev)
+    op = torch.empty(B, dtype=torch.int32, device=dev)
+    e.run_device(pairs_t, init_t, oT, oe, op, epsilon=0.05)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(oT.cpu().numpy().reshape(B, 2, 3), ref.T[:, :2, :])
+    np.testing.assert_array_equal(op.cpu().numpy(), ref.iters)
+    np.testing.assert_array_equal(oe.cpu().numpy(), ref.error)     # deterministic reductions: bit-equal reruns
+
+
+def test_error_behaviour(gicp):
+    a = np.c_[np.random.default_rng(0).uniform(size=(10, 2)), np.ones(10)]
+    with pytest.raises(ValueError):
+        gicp.icp(a[:0], a)                                       # empty cloud
+    with pytest.raises(ValueError):
+        gicp.icp(a[:, :2], a)                                    # not homogeneous
+    with pytest.raises(ValueError):
+        gicp.icp_batch([a[:, :2], a[:0, :2]], [[0, 1]])          # empty scan in the table
+    with pytest.raises(ValueError):
+        gicp.icp_batch([a[:, :2], a[:, :2]], [[0, 2]])           # pair index out of range
+    with pytest.raises(ValueError):
+        bad = a.copy(); bad[3, 0] = np.nan
+        gicp.icp(bad, a)
+    res = gicp.icp_batch([a[:, :2], a[:, :2]], np.zeros((0, 2), dtype=np.int32))
+    assert len(res) == 0

@@ -1,0 +1,81 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/icpb.h declares,
+host-side validation raises before anything is launched, and the product never imports the
+oracle.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "icpb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(icpb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from icp_slam_b200 import _lib
+    so = _lib.build()
+    L = ctypes.CDLL(so)
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(L, s), s
+    assert sorted(_lib.EXPORTS) == syms
+    L.icpb_abi_version.restype = ctypes.c_int
+    assert L.icpb_abi_version() == 1
+
+
+def test_default_params_match_reference_defaults():
+    from icp_slam_b200 import _lib
+    p = _lib.default_params()       # pure host function, no CUDA call
+    assert (p.epsilon, p.max_iters, p.stopping_thresh, p.rotation_only) == (0.01, 100, 0.0001, 0)
+    assert p.hist_cap == 0 and p.corr_stride == 0 and p.pair_mode == 0
+
+
+def test_param_struct_layout_matches_header():
+    from icp_slam_b200 import _lib
+    assert ctypes.sizeof(_lib.IcpbParams) == 2 * 8 + 6 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.IcpbKernelInfo) == 8 * 4
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the product raises; it never falls back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from icp_slam_b200 import icp as gicp
+    a = np.c_[np.random.default_rng(0).uniform(size=(10, 2)), np.ones(10)]
+    with pytest.raises((gicp.IcpbError, RuntimeError)):
+        gicp.icp(a, a)
+
+
+def test_host_validation_precedes_launch():
+    from icp_slam_b200 import icp as gicp
+    a = np.c_[np.random.default_rng(0).uniform(size=(10, 2)), np.ones(10)]
+    with pytest.raises(ValueError):
+        gicp.icp(a[:0], a)
+    with pytest.raises(ValueError):
+        gicp.icp(a[:, :2], a)
+    with pytest.raises(ValueError):
+        gicp.icp(a, a, init_transform=np.eye(4))
+    with pytest.raises(ValueError):
+        gicp.ScanTable([a[:, :2], a[:0, :2]])
+    with pytest.raises(ValueError):
+        gicp.ScanTable(xy=a[:, :2], offsets=[0, 4, 4, 10])
+    t = gicp.ScanTable([a[:, :2], a[:4, :2]])
+    assert t.n_scans == 2 and t.longest == 10 and list(t.offsets) == [0, 10, 14]
+    assert gicp.max_passes(100) == 102 and gicp.max_passes(-3) == 1
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "icp-slam-with-loop-closure_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("no oracle", ""), f
