@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the batched ICP hot path: ICP scan-pair alignments / second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the full odometry ICP chain over a 5,000-scan synthetic
+indoor trajectory, 1,024-beam scans, pairs (i, i-1) with the odometry initial guess, epsilon 0.05,
+max_iters 100 (reference scripts/main.py:240-247).  One step = one pass of the hot path over the
+whole 4,999-pair batch.  With N GPUs every rank aligns its own 4,999-pair chain (weak scaling)
+and an NCCL all-gather returns every pair's constraint record to all ranks.
+
+`value`     device-timed: scan table, pairs and initial guesses already resident in HBM.
+`e2e`       the same step through the public host API (IcpEngine.set_scans + run, i.e. the C
+            ABI's icpb_upload_scans + icpb_run_host): pinned host buffers in, results out.
+`roofline`  FP32-pipe roofline of the alignment kernel: algorithmic
+            point-pair distance evaluations (sum over pairs of passes*N1*N2) per second against
+            SMs * 128 lanes * f_max / 4 instruction slots.
+`cpu_baseline` the C port of the reference algorithm (oracle/icp_oracle.c) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "icp_scan_pair_alignments_per_sec"
+UNIT = "pairs/s"
+SEED = 467002
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scans", type=int, default=5000, help="scans in the chain (config: 5000)")
+    ap.add_argument("--beams", type=int, default=1024, help="beams per scan (config: 1024)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
+    return ap.parse_args()
+
+
+def workload(args, rank, world):
+    from icp_slam_b200 import synth
+    # each rank owns a different stretch of the trajectory and its own noise/odometry seed
+    rng_seed = SEED + 1000 * rank
+    rng = np.random.default_rng(rng_seed)
+    poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=rank / max(world, 1))
+    scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
+    odo = synth.odometry_from_truth(poses, rng)
+    idx = np.arange(1, args.scans)
+    pairs = np.stack((idx, idx - 1), axis=1).astype(np.int32)
+    init = np.stack([synth.pose_to_mat(odo[i] - odo[i - 1]) for i in idx])
+    return scans, pairs, init
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (profiling guide)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_rate(scans, pairs, init, seconds, threads=0):
+    """Time the C port of the reference algorithm on a bounded sample of the same workload."""
+    from oracle import c_oracle
+    c_oracle.build()
+    nthr = threads or c_oracle.max_threads()
+    xy, off = c_oracle.pack(scans)
+    rng = np.random.default_rng(SEED)
+    order = rng.permutation(len(pairs))
+    probe = order[:max(2 * nthr, 8)]
+    t = time.perf_counter()
+    c_oracle.icp_batch(xy, off, pairs[probe], init[probe], epsilon=0.05, max_iters=100, n_threads=nthr)
+    dt = time.perf_counter() - t
+    n = int(min(len(pairs), max(len(probe), len(probe) * seconds / max(dt, 1e-3))))
+    sel = order[:n]
+    t = time.perf_counter()
+    _, _, passes = c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=0.05, max_iters=100, n_threads=nthr)
+    dt = time.perf_counter() - t
+    return n / dt, nthr, n, dt, float(passes.mean())
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
+    Python and is not present on the GPU box, so this times its C port (oracle/icp_oracle.c, the
+    one place besides cpu_baseline where bench.py executes oracle/) on all host cores."""
+    if rank != 0:
+        return
+    scans, pairs, init = workload(args, 0, 1)
+    from oracle import c_oracle
+    c_oracle.build()
+    nthr = c_oracle.max_threads()
+    xy, off = c_oracle.pack(scans)
+    rng = np.random.default_rng(SEED)
+    order = rng.permutation(len(pairs))
+    # size one step so that warmup + steps end within ~2 minutes
+    probe = order[:max(2 * nthr, 8)]
+    t = time.perf_counter()
+    c_oracle.icp_batch(xy, off, pairs[probe], init[probe], epsilon=0.05, max_iters=100, n_threads=nthr)
+    dt = time.perf_counter() - t
+    budget = 100.0 / max(args.steps + args.warmup, 1)
+    n = int(min(len(pairs), max(len(probe), len(probe) * budget / max(dt, 1e-3))))
+    sel = order[:n]
+    for _ in range(args.warmup):
+        c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=0.05, max_iters=100, n_threads=nthr)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=0.05, max_iters=100, n_threads=nthr)
+    dt = time.perf_counter() - t
+    rate = n * args.steps / dt
+    sample = f"{n} of {len(pairs)} chain pairs per step, seeded random subsample, {nthr} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"odometry chain {args.scans} scans x {args.beams} beams (configs[1])",
+                   "pairs_per_step": n, "epsilon": 0.05, "max_iters": 100},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from icp_slam_b200 import icp as gicp
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    scans, pairs, init = workload(args, rank, world)
+    B = len(pairs)
+    eng = gicp.IcpEngine(local)
+    table = gicp.ScanTable(scans)
+    # pinned host copies (the e2e leg's sources) and HBM-resident copies (the `value` leg)
+    xy_pin = torch.from_numpy(table.xy).pin_memory()
+    off_pin = torch.from_numpy(table.offsets).pin_memory()
+    pairs_pin = torch.from_numpy(pairs).pin_memory()
+    init6 = np.ascontiguousarray(init[:, :2, :].reshape(B, 6))
+    init_pin = torch.from_numpy(init6).pin_memory()
+    xy_t, off_t = xy_pin.to(dev), off_pin.to(dev)
+    pairs_t, init_t = pairs_pin.to(dev), init_pin.to(dev)
+    eng.set_scans_device(xy_t, off_t, table)
+    # constraint records: [T(6), err, passes] as 8 float64 per pair
+    rec = torch.empty((B, 8), dtype=torch.float64, device=dev)
+    out_T = torch.empty((B, 6), dtype=torch.float64, device=dev)
+    out_err = torch.empty(B, dtype=torch.float64, device=dev)
+    out_pass = torch.empty(B, dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * B, 8), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device=dev)     # 768 MB > 126 MB L2
+
+    def step_device():
+        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
+        if world > 1:
+            rec[:, :6] = out_T
+            rec[:, 6] = out_err
+            rec[:, 7] = out_pass.to(torch.float64)
+            dist.all_gather_into_tensor(gathered, rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush.fill_(float(k))                   # evict L2 between timed iterations (outside the events)
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record()
+        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
+        ev[k][1].record()
+        if world > 1:
+            rec[:, :6] = out_T
+            rec[:, 6] = out_err
+            rec[:, 7] = out_pass.to(torch.float64)
+            dist.all_gather_into_tensor(gathered, rec)
+        ev[k][2].record()
+    barrier()
+    t_wall1 = time.time()
+    launches = eng.launch_count - launches0
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # work actually done (exact: passes per pair come back from the kernel)
+    passes = out_pass.cpu().numpy().astype(np.int64)
+    lens = table.lengths
+    work = float(np.sum(passes * lens[pairs[:, 0]] * lens[pairs[:, 1]]))          # PDE per step on this rank
+    info = eng.kernel_info(B)
+
+    # ---- e2e: the public host API with pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        tab_pin = gicp.ScanTable(xy=xy_pin.numpy(), offsets=off_pin.numpy())
+        pairs_h, init_h = pairs_pin.numpy(), init
+        eng2 = gicp.IcpEngine(local)
+
+        def step_host():
+            eng2.set_scans(tab_pin)
+            return eng2.run(pairs_h, init_h, epsilon=0.05, max_iters=100)
+
+        for _ in range(max(args.warmup, 1)):
+            res = step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step_host()
+            if world > 1:                        # the gather of constraint records, from host results
+                rec[:, :6].copy_(torch.from_numpy(res.T[:, :2, :].reshape(B, 6)))
+                dist.all_gather_into_tensor(gathered, rec)
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        h2d = table.xy.nbytes + table.offsets.nbytes + pairs.nbytes + init6.nbytes
+        d2h = B * (6 * 8 + 8 + 4)
+        e2e = {"value": world * B * args.steps / float(t_e2e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(t_e2e.item()) / args.steps * 1e3}
+        assert np.array_equal(res.iters, passes.astype(np.int32))
+        eng2.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        sm_count = info["sm_count"]
+        kern_s = float(kern_ms.mean()) * 1e-3
+        pde_peak = sm_count * 128 * sm_max_mhz * 1e6 / 4.0                 # FP32-pipe slots / 4 per PDE
+        achieved = work / kern_s
+        alg_bytes = float(np.sum(16.0 * (lens[pairs[:, 0]] + lens[pairs[:, 1]]) + 60.0 + 56.0))
+        roofline = {
+            "bound": "fp32_pipe", "achieved": achieved * 1e-12, "peak": pde_peak * 1e-12, "unit": "TPDE/s",
+            "frac": achieved / pde_peak, "traffic": None,
+            "definition": "PDE = one point-pair distance evaluation = 4 FP32-pipe lane-slots (FADD,FADD,FMUL,FFMA); "
+                          "peak = SMs*128*sm_max_mhz/4 (SURVEY.md 8d formula; clock " + peak_src + ")",
+            "pde_per_launch": work, "kernel_ms": kern_s * 1e3,
+            "flops_view": {"achieved_tflops": achieved * 5e-12, "fma_peak_tflops": sm_count * 128 * 2 * sm_max_mhz * 1e-6},
+            "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kern_s * 1e-9,
+                         "peak_gbs": hbm_peak, "frac": alg_bytes / kern_s * 1e-9 / hbm_peak, "peak_source": peak_src},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            rate, nthr, n, dt, mean_pass = cpu_port_rate(scans, pairs, init, args.cpu_seconds)
+            cpu = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
+                   "sample": f"{n} of {B} chain pairs (seeded random subsample) in {dt:.1f} s, "
+                             f"mean {mean_pass:.1f} passes, C port oracle/icp_oracle.c on {nthr} threads"}
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / total_s, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 filter + f64 decide/accumulate",
+            "data": "synthetic",
+            "config": {"workload": f"odometry chain {args.scans} scans x {args.beams} beams per GPU (configs[1]), "
+                                   f"{B} pairs per GPU per step",
+                       "pairs_per_step": world * B, "epsilon": 0.05, "max_iters": 100,
+                       "mean_passes": float(passes.mean()), "l2": "flushed between timed steps (768 MB fill)",
+                       "collective": "all_gather of (B,8) f64 constraint records" if world > 1 else "none",
+                       "kernel": info},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

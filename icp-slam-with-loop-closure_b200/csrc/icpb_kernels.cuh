@@ -67,6 +67,34 @@ __device__ __forceinline__ void apply_T(const double *T, double x, double y, dou
     oy = fma(T[4], y, T[3] * x) + T[5];
 }
 
+// Packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): two targets per instruction, so the sweep
+// needs 2 issue slots per distance instead of 4.  Each half rounds exactly like the scalar
+// __fsub_rn / __fmul_rn / __fmaf_rn in dist32 (IEEE round-to-nearest, no flush), so the sweep
+// and the refine step see bit-identical filter distances.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// filter distances of one source point to four targets (x0..x3, y0..y3)
+__device__ __forceinline__ void dist32x4(u64 PX, u64 PY, const float4 &X, const float4 &Y, float *d)
+{
+    const u64 dxa = sub2(pack2(X.x, X.y), PX), dya = sub2(pack2(Y.x, Y.y), PY);
+    const u64 dxb = sub2(pack2(X.z, X.w), PX), dyb = sub2(pack2(Y.z, Y.w), PY);
+    unpack2(fma2(dya, dya, mul2(dxa, dxa)), d[0], d[1]);
+    unpack2(fma2(dyb, dyb, mul2(dxb, dxb)), d[2], d[3]);
+}
+
 __device__ __forceinline__ float min3f(float a, float b, float c)
 {
     return fminf(fminf(a, b), c);
@@ -120,7 +148,7 @@ __device__ __forceinline__ void decode_pair(int64_t k, int64_t n, int32_t &i_out
 }
 
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 icp_align_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -224,13 +252,9 @@ icp_align_kernel(const KernelArgs a)
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         float d[16];
+                        const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            d[4 * v + 0] = dist32(px[r], py[r], X[v].x, Y[v].x);
-                            d[4 * v + 1] = dist32(px[r], py[r], X[v].y, Y[v].y);
-                            d[4 * v + 2] = dist32(px[r], py[r], X[v].z, Y[v].z);
-                            d[4 * v + 3] = dist32(px[r], py[r], X[v].w, Y[v].w);
-                        }
+                        for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
                         float cm = min3f(d[0], d[1], d[2]);
                         cm = min3f(cm, d[3], d[4]);
                         cm = min3f(cm, d[5], d[6]);
