@@ -268,6 +268,11 @@ def main():
     lens = table.lengths
     work = float(np.sum(passes * lens[pairs[:, 0]] * lens[pairs[:, 1]]))          # PDE per step on this rank
     info = eng.kernel_info(B)
+    # one instrumented launch (outside every timed region): distance evaluations actually executed
+    eng.count_work(True)
+    eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
+    executed = float(eng.read_work())
+    eng.count_work(False)
 
     # ---- e2e: the public host API with pinned host buffers, copies inside the timed region ----
     e2e = None
@@ -321,6 +326,8 @@ def main():
             "definition": "PDE = one point-pair distance evaluation = 4 FP32-pipe lane-slots (FADD,FADD,FMUL,FFMA); "
                           "peak = SMs*128*sm_max_mhz/4 (SURVEY.md 8d formula; clock " + peak_src + ")",
             "pde_per_launch": work, "kernel_ms": kern_s * 1e3,
+            "executed_pde_per_launch": executed, "executed_share": executed / work,
+            "executed_frac_of_peak": executed / kern_s / pde_peak,
             "flops_view": {"achieved_tflops": achieved * 5e-12, "fma_peak_tflops": sm_count * 128 * 2 * sm_max_mhz * 1e-6},
             "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kern_s * 1e-9,
                          "peak_gbs": hbm_peak, "frac": alg_bytes / kern_s * 1e-9 / hbm_peak, "peak_source": peak_src},

@@ -10,19 +10,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libicpb.so")
 
+FLAG_EXHAUSTIVE = 1
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destroy",
            "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
-           "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error"]
+           "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
+           "icpb_count_work", "icpb_read_work"]
 
 
 class IcpbParams(ctypes.Structure):
     _fields_ = [("epsilon", ctypes.c_double), ("stopping_thresh", ctypes.c_double),
                 ("max_iters", ctypes.c_int32), ("rotation_only", ctypes.c_int32),
                 ("hist_cap", ctypes.c_int32), ("corr_stride", ctypes.c_int32),
-                ("pair_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("pair_mode", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("k_first", ctypes.c_int64), ("k_block", ctypes.c_int64), ("k_stride", ctypes.c_int64)]
 
 
@@ -85,6 +88,8 @@ def lib() -> ctypes.CDLL:
     L.icpb_launch_count.argtypes = [vp]
     L.icpb_launch_count.restype = ctypes.c_int64
     L.icpb_last_error.restype = ctypes.c_char_p
+    L.icpb_count_work.argtypes = [vp, ctypes.c_int]
+    L.icpb_read_work.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

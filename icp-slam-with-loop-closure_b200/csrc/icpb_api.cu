@@ -52,8 +52,15 @@ struct DevBuf {
 };
 
 struct LaunchCfg {
-    int threads, smem, n2pad_cap, n1_cap, ctas_per_sm;
+    int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ctas_per_sm;
 };
+
+typedef void (*kernel_fn)(const icpb::KernelArgs);
+kernel_fn pick_kernel(const icpb_params *p)
+{
+    return (p && (p->flags & ICPB_FLAG_EXHAUSTIVE)) ? icpb::icp_align_kernel<kPointsPerThread, false>
+                                                    : icpb::icp_align_kernel<kPointsPerThread, true>;
+}
 
 }  // namespace
 
@@ -66,7 +73,8 @@ struct icpb_ctx {
     int64_t n_scans = 0, longest = 0;
     DevBuf own_xy, own_off;
     // queue counters
-    unsigned long long *queue = nullptr;
+    unsigned long long *queue = nullptr;      // kQueueRing counters, then one work counter
+    unsigned long long *executed = nullptr;   // non-null while work counting is enabled
     int64_t launches = 0;
     // scratch for host-pointer entry points
     DevBuf s_pairs, s_init, s_T, s_err, s_passes, s_hist, s_corr, s_pair_xy, s_pair_off;
@@ -76,12 +84,13 @@ struct icpb_ctx {
 
 namespace {
 
-int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c)
+int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c, kernel_fn fn)
 {
     if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
     const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
     const int64_t n1c = (longest + 3) & ~int64_t(3);
-    const int64_t smem = 8 * n2pad + 4 * n1c + 8 * (icpb::kMaxWarps * icpb::kNumSums + 8);
+    const int64_t nchunk = n2pad / icpb::kChunk;
+    const int64_t smem = 8 * n2pad + 16 * nchunk + 4 * n1c + 8 * (2 * icpb::kMaxWarps * icpb::kNumSums);
     if (smem > kMaxSmem) {
         snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
                  (long long)longest, (long long)smem, kMaxSmem);
@@ -92,14 +101,16 @@ int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c)
     if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
     c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
+    c->nchunk_cap = (int)nchunk;
     if ((int)smem > h->max_smem_set) {
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread>,
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->max_smem_set = (int)smem;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icpb::icp_align_kernel<kPointsPerThread>,
-                                                     threads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     if (per_sm < 1) return fail(ICPB_EINVAL, "kernel does not fit on an SM%s");
     c->ctas_per_sm = per_sm;
     return 0;
@@ -123,7 +134,8 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
-    int rc = make_cfg(h, longest, &cfg);
+    kernel_fn fn = pick_kernel(p);
+    int rc = make_cfg(h, longest, &cfg, fn);
     if (rc) return rc;
     icpb::KernelArgs a;
     a.xy = xy; a.offsets = offsets; a.pairs = d_pairs; a.init = d_init; a.B = B; a.n_scans = n_scans;
@@ -132,11 +144,12 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.hist = p->hist_cap > 0 ? d_hist : nullptr;
     a.corr = p->corr_stride > 0 ? d_corr : nullptr;
     a.queue = h->queue + (h->launches % kQueueRing);
-    a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap;
+    a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap;
+    a.executed = h->executed;
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
     if (grid > B) grid = B;
-    icpb::icp_align_kernel<kPointsPerThread><<<(unsigned)grid, cfg.threads, cfg.smem, stream>>>(a);
+    fn<<<(unsigned)grid, cfg.threads, cfg.smem, stream>>>(a);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
@@ -178,7 +191,8 @@ int icpb_create(int device, icpb_handle *out)
     if (!h) return fail(ICPB_EINVAL, "out of host memory%s");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    cudaError_t e = cudaMalloc(&h->queue, sizeof(unsigned long long) * kQueueRing);
+    cudaError_t e = cudaMalloc(&h->queue, sizeof(unsigned long long) * (kQueueRing + 1));
+    if (e == cudaSuccess) e = cudaMemset(h->queue, 0, sizeof(unsigned long long) * (kQueueRing + 1));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "icpb_create: %s", cudaGetErrorString(e));
@@ -365,18 +379,43 @@ int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out)
     if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
     CU(cudaSetDevice(h->device));
     LaunchCfg cfg;
-    int rc = make_cfg(h, h->longest, &cfg);
+    kernel_fn fn = pick_kernel(nullptr);
+    int rc = make_cfg(h, h->longest, &cfg, fn);
     if (rc) return rc;
     cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, icpb::icp_align_kernel<kPointsPerThread>));
+    CU(cudaFuncGetAttributes(&fa, fn));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
     if (B > 0 && grid > B) grid = B;
     out->threads_per_cta = cfg.threads; out->ctas_per_sm = cfg.ctas_per_sm; out->sm_count = h->sm_count;
     out->grid = (int32_t)grid; out->regs_per_thread = fa.numRegs; out->smem_bytes = cfg.smem;
-    out->points_per_thread = kPointsPerThread; out->variant = 1;
+    out->points_per_thread = kPointsPerThread; out->variant = 2;
     return 0;
 }
 
 int64_t icpb_launch_count(icpb_handle h) { return h ? h->launches : 0; }
+
+int icpb_count_work(icpb_handle h, int enable)
+{
+    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
+    CU(cudaSetDevice(h->device));
+    if (enable) {
+        CU(cudaMemset(h->queue + kQueueRing, 0, sizeof(unsigned long long)));
+        h->executed = h->queue + kQueueRing;
+    } else {
+        h->executed = nullptr;
+    }
+    return 0;
+}
+
+int icpb_read_work(icpb_handle h, uint64_t *executed_pde)
+{
+    if (!h || !executed_pde) return fail(ICPB_EINVAL, "icpb_read_work: bad argument%s");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, h->queue + kQueueRing, sizeof v, cudaMemcpyDeviceToHost));
+    *executed_pde = v;
+    return 0;
+}
 
 }  // extern "C"

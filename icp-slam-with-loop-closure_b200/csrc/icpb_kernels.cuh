@@ -13,6 +13,11 @@
 //     all-fp64 search, and fp32 only decides how much fp64 work is needed;
 //   * transform application, centroids, cross-covariance, error, composition and the stop
 //     rules are fp64, reduced in a fixed order (deterministic).
+//   * Exact pruning: 16-target chunks carry a bounding circle; a warp skips a chunk only when the
+//     triangle inequality proves that every target in it is farther from every one of the warp's
+//     128 source points than that point's current upper bound (its filter distance to the
+//     previous pass's match) plus the rounding bound.  Skipped targets can therefore never be a
+//     candidate of the exact decision, so the result is that of the exhaustive search.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,6 +46,8 @@ struct KernelArgs {
     unsigned long long *queue;// work-queue counter (zeroed before launch)
     int32_t        n2pad_cap; // floats per target coordinate array in shared memory
     int32_t        n1_cap;    // int32 slots for correspondences in shared memory
+    int32_t        nchunk_cap;// chunk bounding circles in shared memory
+    unsigned long long *executed; // optional: += distance evaluations actually executed
 };
 
 // ---- fp32 filter distance: one definition, used by the sweep and by the refine step ----------
@@ -147,21 +154,38 @@ __device__ __forceinline__ void decode_pair(int64_t k, int64_t n, int32_t &i_out
     j_out = (int32_t)(k - start + i + 1);
 }
 
-template <int R>
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// PRUNE = false: exhaustive sweep over every chunk (the reference's brute force; used for the
+// FP32-pipe roofline characterisation).  PRUNE = true: exact chunk pruning (the product default).
+template <int R, bool PRUNE>
 __global__ void __launch_bounds__(256, 3)
 icp_align_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float  *tqx    = reinterpret_cast<float *>(smem_raw);
     float  *tqy    = tqx + a.n2pad_cap;
-    int    *corr_s = reinterpret_cast<int *>(tqy + a.n2pad_cap);
-    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // 16B aligned
-    double *ctl    = red + kMaxWarps * kNumSums;     // [0..5] T, [6] err, [7] done flag
+    float4 *cb     = reinterpret_cast<float4 *>(tqy + a.n2pad_cap);          // chunk circle (cx, cy, r, -)
+    int    *corr_s = reinterpret_cast<int *>(cb + a.nchunk_cap);
+    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // [2][kMaxWarps][9]
     __shared__ long long s_pid;
     __shared__ unsigned int s_qmax_bits;
 
     const int tid = threadIdx.x, NT = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const float kInf = __int_as_float(0x7f800000);
+    unsigned long long executed = 0;
 
     for (;;) {
         // ---------------- pop a problem ----------------
@@ -171,7 +195,7 @@ icp_align_kernel(const KernelArgs a)
         }
         __syncthreads();
         const int64_t pid = s_pid;
-        if (pid >= a.B) return;
+        if (pid >= a.B) break;
 
         int32_t sid, did;
         if (a.p.pair_mode == 1) {
@@ -202,74 +226,137 @@ icp_align_kernel(const KernelArgs a)
                 }
                 tqx[j] = x; tqy[j] = y;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, o));
+            qm = warp_max(qm);
             if (lane == 0) atomicMax(&s_qmax_bits, __float_as_uint(qm));   // qm >= 0: bit order = value order
-        }
-        if (tid < 6) {
-            double v = a.init ? a.init[6 * pid + tid] : ((tid == 0 || tid == 4) ? 1.0 : 0.0);
-            if (a.p.rotation_only && (tid == 2 || tid == 5)) v = 0.0;       // src/icp.py:60-61
-            ctl[tid] = v;
         }
         __syncthreads();
         const float qmax = __uint_as_float(s_qmax_bits);
+        // ---------------- bounding circle of every 16-target chunk ----------------
+        for (int c = tid; c < nchunks; c += NT) {
+            const int j0 = c * kChunk, j1 = min(j0 + kChunk, n2);
+            float lx = kInf, ly = kInf, hx = -kInf, hy = -kInf;
+            for (int j = j0; j < j1; ++j) {
+                lx = fminf(lx, tqx[j]); hx = fmaxf(hx, tqx[j]);
+                ly = fminf(ly, tqy[j]); hy = fmaxf(hy, tqy[j]);
+            }
+            const float cx = 0.5f * (lx + hx), cy = 0.5f * (ly + hy);
+            float r2 = 0.0f;
+            for (int j = j0; j < j1; ++j) r2 = fmaxf(r2, dist32(cx, cy, tqx[j], tqy[j]));
+            cb[c] = make_float4(cx, cy, sqrtf(r2) * 1.00001f, 0.0f);
+        }
+        double T[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = a.init ? a.init[6 * pid + k] : ((k == 0 || k == 4) ? 1.0 : 0.0);
+            if (a.p.rotation_only && (k == 2 || k == 5)) v = 0.0;          // src/icp.py:60-61
+            T[k] = v;
+        }
         const double2 g = dst[0];                 // shift for the one-pass covariance sums
+        const double2 s0 = src[0];
+        __syncthreads();
 
         int passes = 0, iteration = 0;
         bool have_last = false;
-        double last_err = 0.0;
+        double last_err = 0.0, err = 0.0;
 
         for (;;) {
-            double T[6];
+            double cx, cy;                                   // shift = transformed first source point
+            apply_T(T, s0.x, s0.y, cx, cy);
+            double sum[kNumSums];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) T[k] = ctl[k];
+            for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
 
-            // =========== P1: nearest neighbours (src/icp.py:10-19) ===========
             for (int base = 0; base < n1; base += NT * R) {
                 if (base + warp * 32 * R >= n1) break;          // this warp has no points in the tile
                 const int i0 = base + tid * R;
+                // ---- transform, upper bounds, tile bounding circle ----
                 float px[R], py[R];
+                float ubmax = 0.0f, lx = kInf, ly = kInf, hx = -kInf, hy = -kInf;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int i = min(i0 + r, n1 - 1);
+                    const int i = min(i0 + r, n1 - 1);           // lanes past the end repeat the last point
                     const double2 s = src[i];
                     double X, Y;
                     apply_T(T, s.x, s.y, X, Y);
                     px[r] = (float)X; py[r] = (float)Y;
+                    if (PRUNE) {
+                        float ub = kInf;
+                        if (passes > 0) {
+                            const int j = corr_s[i];             // previous pass's match: a real target
+                            ub = dist32(px[r], py[r], tqx[j], tqy[j]);
+                        } else {
+                            for (int c = 0; c < nchunks; ++c)    // first pass: every 16th target
+                                ub = fminf(ub, dist32(px[r], py[r], tqx[c * kChunk], tqy[c * kChunk]));
+                        }
+                        ubmax = fmaxf(ubmax, ub + filter_tol(ub, px[r], py[r], qmax));
+                        lx = fminf(lx, px[r]); hx = fmaxf(hx, px[r]);
+                        ly = fminf(ly, py[r]); hy = fmaxf(hy, py[r]);
+                    }
                 }
+                float tcx = 0.f, tcy = 0.f, reach = kInf;
+                if (PRUNE) {
+                    lx = warp_min(lx); ly = warp_min(ly); hx = warp_max(hx); hy = warp_max(hy);
+                    tcx = 0.5f * (lx + hx); tcy = 0.5f * (ly + hy);
+                    float rho2 = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) rho2 = fmaxf(rho2, dist32(tcx, tcy, px[r], py[r]));
+                    rho2 = warp_max(rho2);
+                    ubmax = warp_max(ubmax);
+                    // every target within sqrt(ubmax) of some point of the tile lies within `reach`
+                    // of the tile centre; 4e covers the fp32 rounding of the centres and differences
+                    const float e = 4.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))) + qmax);
+                    reach = (sqrtf(rho2) + sqrtf(ubmax)) * 1.00001f + e;
+                }
+
                 float m1[R], m2[R];
                 int c1[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) { m1[r] = __int_as_float(0x7f800000); m2[r] = m1[r]; c1[r] = 0; }
+                for (int r = 0; r < R; ++r) { m1[r] = kInf; m2[r] = kInf; c1[r] = 0; }
 
                 const float4 *qx4 = reinterpret_cast<const float4 *>(tqx);
                 const float4 *qy4 = reinterpret_cast<const float4 *>(tqy);
+                for (int cbase = 0; cbase < nchunks; cbase += 32) {
+                    unsigned need;
+                    {
+                        const int c = cbase + lane;
+                        bool nd = c < nchunks;
+                        if (PRUNE && nd) {
+                            const float4 b = cb[c];
+                            const float lim = (reach + b.z) * 1.00001f;
+                            nd = dist32(tcx, tcy, b.x, b.y) <= lim * lim;
+                        }
+                        need = __ballot_sync(0xffffffffu, nd);
+                    }
+                    executed += (unsigned)__popc(need);
 #pragma unroll 1
-                for (int c = 0; c < nchunks; ++c) {
-                    float4 X[4], Y[4];
+                    while (need) {
+                        const int c = cbase + __ffs(need) - 1;
+                        need &= need - 1;
+                        float4 X[4], Y[4];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
+                        for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float d[16];
-                        const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
+                        for (int r = 0; r < R; ++r) {
+                            float d[16];
+                            const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
-                        float cm = min3f(d[0], d[1], d[2]);
-                        cm = min3f(cm, d[3], d[4]);
-                        cm = min3f(cm, d[5], d[6]);
-                        cm = min3f(cm, d[7], d[8]);
-                        cm = min3f(cm, d[9], d[10]);
-                        cm = min3f(cm, d[11], d[12]);
-                        cm = min3f(cm, d[13], d[14]);
-                        cm = fminf(cm, d[15]);
-                        const bool better = cm < m1[r];
-                        m2[r] = fminf(m2[r], better ? m1[r] : cm);
-                        m1[r] = fminf(m1[r], cm);
-                        c1[r] = better ? c : c1[r];
+                            for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
+                            float cm = min3f(d[0], d[1], d[2]);
+                            cm = min3f(cm, d[3], d[4]);
+                            cm = min3f(cm, d[5], d[6]);
+                            cm = min3f(cm, d[7], d[8]);
+                            cm = min3f(cm, d[9], d[10]);
+                            cm = min3f(cm, d[11], d[12]);
+                            cm = min3f(cm, d[13], d[14]);
+                            cm = fminf(cm, d[15]);
+                            const bool better = cm < m1[r];
+                            m2[r] = fminf(m2[r], better ? m1[r] : cm);
+                            m1[r] = fminf(m1[r], cm);
+                            c1[r] = better ? c : c1[r];
+                        }
                     }
                 }
-                // ---- refine: exact fp64 decision among the filter's candidates ----
+                // ---- exact decision among the filter's candidates, then the fit sums ----
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int i = i0 + r;
@@ -278,117 +365,110 @@ icp_align_kernel(const KernelArgs a)
                         double Px, Py;
                         apply_T(T, s.x, s.y, Px, Py);
                         const float thr = m1[r] + filter_tol(m1[r], px[r], py[r], qmax);
-                        double best = __longlong_as_double(0x7ff0000000000000LL);
-                        int idx = c1[r] * kChunk < n2 ? c1[r] * kChunk : 0;
-                        if (m2[r] <= thr)
-                            refine_range(0, n2, thr, px[r], py[r], Px, Py, tqx, tqy, dst, best, idx);
-                        else
-                            refine_range(c1[r] * kChunk, min(c1[r] * kChunk + kChunk, n2), thr, px[r], py[r],
-                                         Px, Py, tqx, tqy, dst, best, idx);
+                        const int j0 = c1[r] * kChunk;
+                        int idx = j0 < n2 ? j0 : 0;
+                        // candidates inside the best chunk (bit k: target j0 + k)
+                        unsigned cand = 0;
+#pragma unroll
+                        for (int k = 0; k < kChunk; ++k)
+                            cand |= (dist32(px[r], py[r], tqx[j0 + k], tqy[j0 + k]) <= thr ? 1u : 0u) << k;
+                        if (m2[r] > thr && __popc(cand) == 1) {
+                            idx = j0 + __ffs(cand) - 1;              // unique candidate: no fp64 needed
+                        } else {
+                            double best = __longlong_as_double(0x7ff0000000000000LL);
+                            if (m2[r] <= thr)
+                                refine_range(0, n2, thr, px[r], py[r], Px, Py, tqx, tqy, dst, best, idx);
+                            else
+                                refine_range(j0, min(j0 + kChunk, n2), thr, px[r], py[r], Px, Py,
+                                             tqx, tqy, dst, best, idx);
+                        }
                         corr_s[i] = idx;
+                        const double2 q = dst[idx];
+                        const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
+                        sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
+                        sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
+                        sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
+                        const double ex = Px - q.x, ey = Py - q.y;
+                        sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
                     }
                 }
             }
-            __syncthreads();
 
-            // =========== P2: sums for the rigid fit and the error (src/icp.py:22-52) ===========
-            double cx, cy;                                   // shift = transformed first source point
-            {
-                const double2 s0 = src[0];
-                apply_T(T, s0.x, s0.y, cx, cy);
-            }
-            double sum[kNumSums];
-#pragma unroll
-            for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
-            for (int i = tid; i < n1; i += NT) {
-                const double2 s = src[i];
-                double Px, Py;
-                apply_T(T, s.x, s.y, Px, Py);
-                const double2 q = dst[corr_s[i]];
-                const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
-                sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
-                sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
-                sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
-                const double ex = Px - q.x, ey = Py - q.y;
-                sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
-            }
+            // =========== fit (src/icp.py:22-52): deterministic reduction, one barrier per pass ===========
+            double *redp = red + (passes & 1) * (kMaxWarps * kNumSums);
 #pragma unroll
             for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < kNumSums; ++k) red[warp * kNumSums + k] = sum[k];
+                for (int k = 0; k < kNumSums; ++k) redp[warp * kNumSums + k] = sum[k];
             }
             __syncthreads();
-
-            if (warp == 0) {
-                // fixed-order cross-warp sum: lane k (< 9) adds column k over the warps in order
-                double tot = 0.0;
-                if (lane < kNumSums)
-                    for (int w = 0; w < nwarps; ++w) tot += red[w * kNumSums + lane];
-                double S[kNumSums];
+            // every thread folds the warp partials in the same fixed order and updates its own T
+            double S[kNumSums];
 #pragma unroll
-                for (int k = 0; k < kNumSums; ++k) S[k] = __shfl_sync(0xffffffffu, tot, k);
-                if (lane == 0) {
-                    const double n = (double)n1;
-                    const double ma_x = S[0] / n, ma_y = S[1] / n, mb_x = S[2] / n, mb_y = S[3] / n;
-                    // centred cross-covariance S = X Y^T (src/icp.py:29-32)
-                    const double s00 = S[4] - S[0] * mb_x, s01 = S[5] - S[0] * mb_y;
-                    const double s10 = S[6] - S[1] * mb_x, s11 = S[7] - S[1] * mb_y;
-                    // rotation maximising tr(R S): closed form of the SVD + det fix (src/icp.py:33-38)
-                    const double A = s00 + s11, Bv = s01 - s10;
-                    const double h = hypot(A, Bv);
-                    double c = 1.0, s = 0.0;
-                    if (h > 0.0) { c = A / h; s = Bv / h; }
-                    const double xbar = cx + ma_x, ybar = cy + ma_y;       // mean of moved source
-                    const double qbx = g.x + mb_x, qby = g.y + mb_y;       // mean of matched target
-                    double tx = qbx - (c * xbar - s * ybar);               // src/icp.py:39
-                    double ty = qby - (s * xbar + c * ybar);
-                    if (a.p.rotation_only) { tx = 0.0; ty = 0.0; }         // src/icp.py:65-66
-                    double N[6];                                           // inc @ T (src/icp.py:67)
-                    N[0] = c * T[0] - s * T[3];
-                    N[1] = c * T[1] - s * T[4];
-                    N[2] = c * T[2] - s * T[5] + tx;
-                    N[3] = s * T[0] + c * T[3];
-                    N[4] = s * T[1] + c * T[4];
-                    N[5] = s * T[2] + c * T[5] + ty;
-                    const double err = S[8];
+            for (int k = 0; k < kNumSums; ++k) S[k] = 0.0;
+            for (int w = 0; w < nwarps; ++w) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) ctl[k] = N[k];
-                    ctl[6] = err;
-                    if (a.hist && passes < a.p.hist_cap) {
-                        double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) hrow[k] = N[k];
-                    }
-                    // stop rules, in the reference's order (src/icp.py:86-95)
-                    bool done = err < a.p.epsilon;
-                    if (!done) done = iteration > a.p.max_iters;
-                    if (!done && have_last) done = fabs(last_err - err) < a.p.stopping_thresh;
-                    ctl[7] = done ? 1.0 : 0.0;
-                }
+                for (int k = 0; k < kNumSums; ++k) S[k] += redp[w * kNumSums + k];
             }
-            __syncthreads();
+            {
+                const double n = (double)n1;
+                const double ma_x = S[0] / n, ma_y = S[1] / n, mb_x = S[2] / n, mb_y = S[3] / n;
+                // centred cross-covariance S = X Y^T (src/icp.py:29-32)
+                const double s00 = S[4] - S[0] * mb_x, s01 = S[5] - S[0] * mb_y;
+                const double s10 = S[6] - S[1] * mb_x, s11 = S[7] - S[1] * mb_y;
+                // rotation maximising tr(R S): closed form of the SVD + det fix (src/icp.py:33-38)
+                const double A = s00 + s11, Bv = s01 - s10;
+                const double h = hypot(A, Bv);
+                double c = 1.0, s = 0.0;
+                if (h > 0.0) { c = A / h; s = Bv / h; }
+                const double xbar = cx + ma_x, ybar = cy + ma_y;       // mean of moved source
+                const double qbx = g.x + mb_x, qby = g.y + mb_y;       // mean of matched target
+                double tx = qbx - (c * xbar - s * ybar);               // src/icp.py:39
+                double ty = qby - (s * xbar + c * ybar);
+                if (a.p.rotation_only) { tx = 0.0; ty = 0.0; }         // src/icp.py:65-66
+                double N[6];                                           // inc @ T (src/icp.py:67)
+                N[0] = c * T[0] - s * T[3];
+                N[1] = c * T[1] - s * T[4];
+                N[2] = c * T[2] - s * T[5] + tx;
+                N[3] = s * T[0] + c * T[3];
+                N[4] = s * T[1] + c * T[4];
+                N[5] = s * T[2] + c * T[5] + ty;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) T[k] = N[k];
+                err = S[8];
+            }
+            if (tid == 0 && a.hist && passes < a.p.hist_cap) {
+                double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) hrow[k] = T[k];
+            }
             ++passes;
-            const double err = ctl[6];
-            const bool done = ctl[7] != 0.0;
-            if (done) {
-                if (tid == 0) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = ctl[k];
-                    a.err_out[pid] = err;
-                    a.passes_out[pid] = passes;
-                }
-                if (a.corr) {
-                    int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;
-                    const int lim = min(n1, a.p.corr_stride);
-                    for (int i = tid; i < lim; i += NT) crow[i] = corr_s[i];
-                }
-                break;
-            }
+            // stop rules, in the reference's order (src/icp.py:86-95)
+            bool done = err < a.p.epsilon;
+            if (!done) done = iteration > a.p.max_iters;
+            if (!done && have_last) done = fabs(last_err - err) < a.p.stopping_thresh;
+            if (done) break;
             last_err = err; have_last = true;
             ++iteration;
         }
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = T[k];
+            a.err_out[pid] = err;
+            a.passes_out[pid] = passes;
+        }
+        if (a.corr) {
+            int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;
+            const int lim = min(n1, a.p.corr_stride);
+            for (int i = tid; i < lim; i += NT) crow[i] = corr_s[i];
+        }
         __syncthreads();        // smem is reused by the next problem
+    }
+    if (a.executed) {
+        // chunks processed by this warp x 16 targets x 128 source-point slots
+        executed = executed * (unsigned long long)(kChunk * 32 * R);
+        if (lane == 0 && executed) atomicAdd(a.executed, executed);
     }
 }
 

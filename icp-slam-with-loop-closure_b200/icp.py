@@ -115,8 +115,9 @@ def _ptr(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
-def _params(epsilon, max_iters, stopping_thresh, rotation_only) -> _lib.IcpbParams:
+def _params(epsilon, max_iters, stopping_thresh, rotation_only, exhaustive=False) -> _lib.IcpbParams:
     p = _lib.default_params()
+    p.flags = _lib.FLAG_EXHAUSTIVE if exhaustive else 0
     p.epsilon = float(epsilon)
     p.stopping_thresh = float(stopping_thresh)
     mi = int(max_iters)
@@ -180,10 +181,12 @@ class IcpEngine:
     # -- host-buffer run (the reference-facing call) -----------------------------------------
     def run(self, pairs, init_transforms=None, epsilon=0.01, max_iters=100, stopping_thresh=0.0001,
             rotation_only=False, return_history=False, return_correspondences=False,
-            all_pairs: tuple | None = None) -> BatchResult:
+            all_pairs: tuple | None = None, exhaustive: bool = False) -> BatchResult:
+        """`exhaustive=True` sweeps every target for every source point (the reference's brute
+        force) instead of the default exact chunk pruning; the results are identical."""
         if self.table is None:
             raise ValueError("no scan table set")
-        p = _params(epsilon, max_iters, stopping_thresh, rotation_only)
+        p = _params(epsilon, max_iters, stopping_thresh, rotation_only, exhaustive)
         if all_pairs is not None:
             # (k_first, k_block, k_stride, B): linear indices over i<j decoded on the device
             p.pair_mode = 1
@@ -228,11 +231,11 @@ class IcpEngine:
     # -- device-buffer run (inputs and outputs resident in HBM; torch tensors) ---------------
     def run_device(self, pairs_t, init_t, out_T, out_err, out_passes, epsilon=0.01, max_iters=100,
                    stopping_thresh=0.0001, rotation_only=False, all_pairs: tuple | None = None,
-                   stream=None):
+                   stream=None, exhaustive: bool = False):
         """Asynchronous launch on torch's current stream (or `stream`, a raw cudaStream_t int).
         pairs_t (B,2) int32, init_t (B,6) float64 or None, outputs (B,6) f64, (B,) f64, (B,) i32."""
         import torch
-        p = _params(epsilon, max_iters, stopping_thresh, rotation_only)
+        p = _params(epsilon, max_iters, stopping_thresh, rotation_only, exhaustive)
         if all_pairs is not None:
             p.pair_mode = 1
             p.k_first, p.k_block, p.k_stride, B = (int(v) for v in all_pairs)
@@ -280,6 +283,15 @@ class IcpEngine:
     @property
     def launch_count(self) -> int:
         return int(self._L.icpb_launch_count(self._h))
+
+    def count_work(self, enable: bool = True):
+        """Instrumentation: count the distance evaluations launches actually execute."""
+        _lib.check(self._L.icpb_count_work(self._h, 1 if enable else 0), "icpb_count_work")
+
+    def read_work(self) -> int:
+        v = ctypes.c_uint64()
+        _lib.check(self._L.icpb_read_work(self._h, ctypes.byref(v)), "icpb_read_work")
+        return int(v.value)
 
 
 _engines: dict = {}

@@ -35,6 +35,12 @@ extern "C" {
 #define ICPB_ETOOLONG 10002   /* a scan does not fit the kernel's shared-memory staging       */
 #define ICPB_ENOSCANS 10003   /* run called before a scan table was set                       */
 
+/* icpb_params.flags: sweep every target for every source point (the reference's brute force,
+ * src/icp.py:10-19) instead of skipping target chunks that provably cannot hold a nearest
+ * neighbour.  Results are identical either way; the flag exists to measure the FP32-pipe
+ * roofline of the unpruned sweep. */
+#define ICPB_FLAG_EXHAUSTIVE 1
+
 typedef struct icpb_ctx *icpb_handle;
 
 /* Keyword arguments of the reference's icp() (src/icp.py:72) plus batch bookkeeping. */
@@ -48,7 +54,7 @@ typedef struct icpb_params {
     int32_t pair_mode;        /* 0: explicit pairs array; 1: all pairs i<j of n_scans, source=j,
                                  target=i (the argument order of src/loop_closure_detection.py:31-34),
                                  decoded on the device from a linear index                    */
-    int32_t reserved;
+    int32_t flags;            /* ICPB_FLAG_* bits                                             */
     /* pair_mode 1 and sharding: problem b of this call is global index
        k = k_first + (b / k_block) * k_stride + (b % k_block); with pair_mode 0 and pairs given
        for this shard only, leave k_first = 0, k_block = B, k_stride = 0.                      */
@@ -117,6 +123,12 @@ int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out);
 
 /* Number of alignment-kernel launches made through this handle (bench.py's gpu_launches). */
 int64_t icpb_launch_count(icpb_handle h);
+
+/* Optional instrumentation: while enabled, launches add the point-pair distance evaluations
+ * they actually execute (after pruning) to a device counter; icpb_read_work synchronises the
+ * device and returns it.  Enabling resets the counter. */
+int icpb_count_work(icpb_handle h, int enable);
+int icpb_read_work(icpb_handle h, uint64_t *executed_pde);
 
 const char *icpb_last_error(void);
 

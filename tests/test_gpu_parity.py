@@ -243,3 +243,42 @@ def test_error_behaviour(gicp):
         gicp.icp(bad, a)
     res = gicp.icp_batch([a[:, :2], a[:, :2]], np.zeros((0, 2), dtype=np.int32))
     assert len(res) == 0
+
+
+@pytest.mark.parametrize("n_beams", [360, 1024])
+def test_pruned_equals_exhaustive(gicp, n_beams):
+    """The exact chunk pruning must not change a single bit of the result, and it must actually
+    skip work on LiDAR-like scans."""
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(99 + n_beams)
+    scans, pairs, init, poses, _ = synth.make_chain_workload(40, n_beams, seed=31 + n_beams)
+    far = np.array([(j, i) for i in range(0, 40, 4) for j in ((i + 13) % 40, (i + 22) % 40)], dtype=np.int32)
+    e = gicp.engine()
+    e.set_scans(scans)
+    for pr, it in ((pairs, init), (far, None)):
+        e.count_work(True)
+        a = e.run(pr, it, epsilon=0.05, max_iters=100, return_correspondences=True)
+        w_pruned = e.read_work()
+        e.count_work(True)
+        b = e.run(pr, it, epsilon=0.05, max_iters=100, return_correspondences=True, exhaustive=True)
+        w_full = e.read_work()
+        e.count_work(False)
+        np.testing.assert_array_equal(a.T, b.T)
+        np.testing.assert_array_equal(a.error, b.error)
+        np.testing.assert_array_equal(a.iters, b.iters)
+        np.testing.assert_array_equal(a.correspondences, b.correspondences)
+        assert w_pruned < (0.6 if n_beams >= 1024 else 0.85) * w_full, (w_pruned, w_full)
+
+
+def test_pruning_on_unordered_clouds(gicp, c_oracle):
+    """Shuffled (spatially incoherent) clouds: pruning finds little to skip but stays exact."""
+    rng = np.random.default_rng(4)
+    dst = rng.uniform(-10, 10, size=(700, 2))
+    src = dst[rng.permutation(700)[:650]] + rng.normal(0, 0.05, size=(650, 2)) + 0.1
+    res = gicp.icp_batch([src, dst], np.array([[0, 1]]), None, epsilon=1e-3, max_iters=30,
+                         return_correspondences=True)
+    T, err, passes, corr = c_oracle.icp_pair(src, dst, None, epsilon=1e-3, max_iters=30)
+    assert res.iters[0] == passes
+    np.testing.assert_array_equal(res.correspondences[0, :650], corr)
+    dt, dth = pose_diff(res.T[0], T)
+    assert dt < POSE_TOL and dth < POSE_TOL
