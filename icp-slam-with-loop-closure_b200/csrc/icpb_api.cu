@@ -30,7 +30,7 @@ int fail(int code, const char *fmt, const char *detail = "")
         }                                                                                 \
     } while (0)
 
-constexpr int kPointsPerThread = 4;
+constexpr int kPointsPerThread = 2;
 constexpr int kQueueRing = 64;
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -52,7 +52,7 @@ struct DevBuf {
 };
 
 struct LaunchCfg {
-    int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ctas_per_sm;
+    int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ntile_cap, ctas_per_sm;
 };
 
 typedef void (*kernel_fn)(const icpb::KernelArgs);
@@ -90,18 +90,18 @@ int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c, kernel_fn fn)
     const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
     const int64_t n1c = (longest + 3) & ~int64_t(3);
     const int64_t nchunk = n2pad / icpb::kChunk;
-    const int64_t smem = 8 * n2pad + 16 * nchunk + 4 * n1c + 8 * (2 * icpb::kMaxWarps * icpb::kNumSums);
+    const int64_t ntile = (longest + 32 * kPointsPerThread - 1) / (32 * kPointsPerThread);
+    const int64_t smem = 8 * n2pad + 16 * nchunk + 4 * n1c + 8 * (2 * ntile * icpb::kNumSums + icpb::kMaxWarps * 6);
     if (smem > kMaxSmem) {
         snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
                  (long long)longest, (long long)smem, kMaxSmem);
         return ICPB_ETOOLONG;
     }
-    int threads = (int)((longest + kPointsPerThread - 1) / kPointsPerThread);
-    threads = (threads + 31) / 32 * 32;
+    int threads = (int)(ntile * 32);                      // one warp per tile, up to 8 warps
     if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
     c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
-    c->nchunk_cap = (int)nchunk;
+    c->nchunk_cap = (int)nchunk; c->ntile_cap = (int)ntile;
     if ((int)smem > h->max_smem_set) {
         CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -144,7 +144,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.hist = p->hist_cap > 0 ? d_hist : nullptr;
     a.corr = p->corr_stride > 0 ? d_corr : nullptr;
     a.queue = h->queue + (h->launches % kQueueRing);
-    a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap;
+    a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
     a.executed = h->executed;
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;

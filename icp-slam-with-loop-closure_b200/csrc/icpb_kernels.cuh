@@ -47,6 +47,7 @@ struct KernelArgs {
     int32_t        n2pad_cap; // floats per target coordinate array in shared memory
     int32_t        n1_cap;    // int32 slots for correspondences in shared memory
     int32_t        nchunk_cap;// chunk bounding circles in shared memory
+    int32_t        ntile_cap; // source tiles (32*R points) whose partial sums live in shared memory
     unsigned long long *executed; // optional: += distance evaluations actually executed
 };
 
@@ -117,12 +118,16 @@ __device__ __forceinline__ float filter_tol(float m1, float px, float py, float 
     return 8.0f * sqrtf(m1) * e + 16.0f * e * e + 16.0f * u * m1;
 }
 
-// All targets j in [lo, hi) whose filter distance is <= thr are evaluated exactly; keeps the
-// lexicographic (distance, index) minimum.  j ascends, so strict < keeps the first index.
-__device__ __forceinline__ void refine_range(int lo, int hi, float thr, float px, float py,
-                                             double Px, double Py, const float *tqx, const float *tqy,
-                                             const double2 *dst, double &best, int &idx)
+// Rare path of the decision step: all targets j in [lo, hi) whose filter distance is <= thr are
+// evaluated exactly; returns the lexicographic (distance, index) minimum (j ascends, so strict <
+// keeps the first index = np.argmin's rule).  Not inlined: it runs for a fraction of a percent
+// of the points and would otherwise be replicated per register-tiled point.
+__device__ __noinline__ int exact_decide(int lo, int hi, int fallback, float thr, float px, float py,
+                                         double Px, double Py, const float *tqx, const float *tqy,
+                                         const double2 *dst)
 {
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int idx = fallback;
     for (int j = lo; j < hi; ++j) {
         const float d = dist32(px, py, tqx[j], tqy[j]);
         if (d <= thr) {
@@ -131,6 +136,7 @@ __device__ __forceinline__ void refine_range(int lo, int hi, float thr, float px
             if (D < best) { best = D; idx = j; }
         }
     }
+    return idx;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -169,6 +175,11 @@ __device__ __forceinline__ float warp_min(float v)
 
 // PRUNE = false: exhaustive sweep over every chunk (the reference's brute force; used for the
 // FP32-pipe roofline characterisation).  PRUNE = true: exact chunk pruning (the product default).
+//
+// Shared memory: target SoA | chunk circles | correspondences | red[2][tiles][9] | Tw[warps][6]
+// A tile = 32*R consecutive source points = one warp's register tile.  Warps pull tiles from a
+// shared counter (tiles differ in how many chunks survive pruning); partial sums are stored per
+// tile and folded in tile order, so the result does not depend on which warp ran which tile.
 template <int R, bool PRUNE>
 __global__ void __launch_bounds__(256, 3)
 icp_align_kernel(const KernelArgs a)
@@ -178,20 +189,24 @@ icp_align_kernel(const KernelArgs a)
     float  *tqy    = tqx + a.n2pad_cap;
     float4 *cb     = reinterpret_cast<float4 *>(tqy + a.n2pad_cap);          // chunk circle (cx, cy, r, -)
     int    *corr_s = reinterpret_cast<int *>(cb + a.nchunk_cap);
-    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // [2][kMaxWarps][9]
+    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // [2][ntile_cap][9]
+    double *Tw     = red + 2 * a.ntile_cap * kNumSums;                       // [kMaxWarps][6] per-warp copy of T
     __shared__ long long s_pid;
     __shared__ unsigned int s_qmax_bits;
+    __shared__ int s_tile_ctr[2];
 
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     const float kInf = __int_as_float(0x7f800000);
-    unsigned long long executed = 0;
+    double *Tmine = Tw + warp * 6;
+    unsigned int executed = 0;
 
     for (;;) {
         // ---------------- pop a problem ----------------
         if (tid == 0) {
             s_pid = (long long)atomicAdd(a.queue, 1ULL);
             s_qmax_bits = 0u;
+            s_tile_ctr[0] = 0; s_tile_ctr[1] = 0;
         }
         __syncthreads();
         const int64_t pid = s_pid;
@@ -213,6 +228,8 @@ icp_align_kernel(const KernelArgs a)
         const double2 *dst = reinterpret_cast<const double2 *>(a.xy) + dof;
         const int n2pad = (n2 + kChunk - 1) / kChunk * kChunk;
         const int nchunks = n2pad / kChunk;
+        const double inv_n = 1.0 / (double)n1;
+        const int ntiles = (n1 + 32 * R - 1) / (32 * R);
 
         // ---------------- stage the target in shared memory as fp32 SoA ----------------
         {
@@ -229,6 +246,11 @@ icp_align_kernel(const KernelArgs a)
             qm = warp_max(qm);
             if (lane == 0) atomicMax(&s_qmax_bits, __float_as_uint(qm));   // qm >= 0: bit order = value order
         }
+        if (lane < 6) {
+            double v = a.init ? a.init[6 * pid + lane] : ((lane == 0 || lane == 4) ? 1.0 : 0.0);
+            if (a.p.rotation_only && (lane == 2 || lane == 5)) v = 0.0;     // src/icp.py:60-61
+            Tmine[lane] = v;
+        }
         __syncthreads();
         const float qmax = __uint_as_float(s_qmax_bits);
         // ---------------- bounding circle of every 16-target chunk ----------------
@@ -244,14 +266,7 @@ icp_align_kernel(const KernelArgs a)
             for (int j = j0; j < j1; ++j) r2 = fmaxf(r2, dist32(cx, cy, tqx[j], tqy[j]));
             cb[c] = make_float4(cx, cy, sqrtf(r2) * 1.00001f, 0.0f);
         }
-        double T[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            double v = a.init ? a.init[6 * pid + k] : ((k == 0 || k == 4) ? 1.0 : 0.0);
-            if (a.p.rotation_only && (k == 2 || k == 5)) v = 0.0;          // src/icp.py:60-61
-            T[k] = v;
-        }
-        const double2 g = dst[0];                 // shift for the one-pass covariance sums
+        const double2 g = dst[0];                 // shifts for the one-pass covariance sums
         const double2 s0 = src[0];
         __syncthreads();
 
@@ -260,29 +275,36 @@ icp_align_kernel(const KernelArgs a)
         double last_err = 0.0, err = 0.0;
 
         for (;;) {
-            double cx, cy;                                   // shift = transformed first source point
-            apply_T(T, s0.x, s0.y, cx, cy);
-            double sum[kNumSums];
-#pragma unroll
-            for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+            double *redp = red + (passes & 1) * a.ntile_cap * kNumSums;
 
-            for (int base = 0; base < n1; base += NT * R) {
-                if (base + warp * 32 * R >= n1) break;          // this warp has no points in the tile
-                const int i0 = base + tid * R;
+            for (;;) {
+                int tile = 0;
+                if (lane == 0) tile = atomicAdd(&s_tile_ctr[passes & 1], 1);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile >= ntiles) break;
+                const int i0 = (tile * 32 + lane) * R;
                 // ---- transform, upper bounds, tile bounding circle ----
                 float px[R], py[R];
                 float ubmax = 0.0f, lx = kInf, ly = kInf, hx = -kInf, hy = -kInf;
+                {
+                    double T[6];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int i = min(i0 + r, n1 - 1);           // lanes past the end repeat the last point
-                    const double2 s = src[i];
-                    double X, Y;
-                    apply_T(T, s.x, s.y, X, Y);
-                    px[r] = (float)X; py[r] = (float)Y;
-                    if (PRUNE) {
+                    for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = min(i0 + r, n1 - 1);       // lanes past the end repeat the last point
+                        const double2 s = src[i];
+                        double X, Y;
+                        apply_T(T, s.x, s.y, X, Y);
+                        px[r] = (float)X; py[r] = (float)Y;
+                    }
+                }
+                if (PRUNE) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
                         float ub = kInf;
                         if (passes > 0) {
-                            const int j = corr_s[i];             // previous pass's match: a real target
+                            const int j = corr_s[min(i0 + r, n1 - 1)];   // previous pass's match: a real target
                             ub = dist32(px[r], py[r], tqx[j], tqy[j]);
                         } else {
                             for (int c = 0; c < nchunks; ++c)    // first pass: every 16th target
@@ -303,7 +325,7 @@ icp_align_kernel(const KernelArgs a)
                     rho2 = warp_max(rho2);
                     ubmax = warp_max(ubmax);
                     // every target within sqrt(ubmax) of some point of the tile lies within `reach`
-                    // of the tile centre; 4e covers the fp32 rounding of the centres and differences
+                    // of the tile centre; e covers the fp32 rounding of the centres and differences
                     const float e = 4.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))) + qmax);
                     reach = (sqrtf(rho2) + sqrtf(ubmax)) * 1.00001f + e;
                 }
@@ -357,71 +379,105 @@ icp_align_kernel(const KernelArgs a)
                     }
                 }
                 // ---- exact decision among the filter's candidates, then the fit sums ----
+                double sum[kNumSums];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int i = i0 + r;
-                    if (i < n1) {
-                        const double2 s = src[i];
-                        double Px, Py;
-                        apply_T(T, s.x, s.y, Px, Py);
-                        const float thr = m1[r] + filter_tol(m1[r], px[r], py[r], qmax);
-                        const int j0 = c1[r] * kChunk;
-                        int idx = j0 < n2 ? j0 : 0;
-                        // candidates inside the best chunk (bit k: target j0 + k)
-                        unsigned cand = 0;
+                for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+                {
+                    double T[6];
 #pragma unroll
-                        for (int k = 0; k < kChunk; ++k)
-                            cand |= (dist32(px[r], py[r], tqx[j0 + k], tqy[j0 + k]) <= thr ? 1u : 0u) << k;
-                        if (m2[r] > thr && __popc(cand) == 1) {
-                            idx = j0 + __ffs(cand) - 1;              // unique candidate: no fp64 needed
-                        } else {
-                            double best = __longlong_as_double(0x7ff0000000000000LL);
-                            if (m2[r] <= thr)
-                                refine_range(0, n2, thr, px[r], py[r], Px, Py, tqx, tqy, dst, best, idx);
-                            else
-                                refine_range(j0, min(j0 + kChunk, n2), thr, px[r], py[r], Px, Py,
-                                             tqx, tqy, dst, best, idx);
+                    for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
+                    double cx, cy;                               // shift = transformed first source point
+                    apply_T(T, s0.x, s0.y, cx, cy);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = i0 + r;
+                        if (i < n1) {
+                            const double2 s = src[i];
+                            double Px, Py;
+                            apply_T(T, s.x, s.y, Px, Py);
+                            const float thr = m1[r] + filter_tol(m1[r], px[r], py[r], qmax);
+                            const int j0 = c1[r] * kChunk;
+                            // candidates inside the best chunk: how many, and where
+                            float d[16];
+                            {
+                                const float4 *bx = reinterpret_cast<const float4 *>(tqx + j0);
+                                const float4 *by = reinterpret_cast<const float4 *>(tqy + j0);
+                                const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) dist32x4(PX, PY, bx[v], by[v], d + 4 * v);
+                            }
+                            int cnt = 0, pos = 0;
+#pragma unroll
+                            for (int k = 0; k < kChunk; ++k) {
+                                const bool in = d[k] <= thr;
+                                cnt += in ? 1 : 0;
+                                pos += in ? k : 0;
+                            }
+                            int idx = j0 + pos;                  // unique candidate: no fp64 needed
+                            if (m2[r] <= thr)                    // another chunk is within the bound
+                                idx = exact_decide(0, n2, j0, thr, px[r], py[r], Px, Py, tqx, tqy, dst);
+                            else if (cnt != 1)
+                                idx = exact_decide(j0, min(j0 + kChunk, n2), j0, thr, px[r], py[r], Px, Py,
+                                                   tqx, tqy, dst);
+                            corr_s[i] = idx;
+                            const double2 q = dst[idx];
+                            const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
+                            sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
+                            sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
+                            sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
+                            const double ex = Px - q.x, ey = Py - q.y;
+                            sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
                         }
-                        corr_s[i] = idx;
-                        const double2 q = dst[idx];
-                        const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
-                        sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
-                        sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
-                        sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
-                        const double ex = Px - q.x, ey = Py - q.y;
-                        sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
                     }
+                }
+#pragma unroll
+                for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < kNumSums; ++k) redp[tile * kNumSums + k] = sum[k];
                 }
             }
 
             // =========== fit (src/icp.py:22-52): deterministic reduction, one barrier per pass ===========
-            double *redp = red + (passes & 1) * (kMaxWarps * kNumSums);
-#pragma unroll
-            for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < kNumSums; ++k) redp[warp * kNumSums + k] = sum[k];
-            }
             __syncthreads();
-            // every thread folds the warp partials in the same fixed order and updates its own T
+            if (tid == 0) s_tile_ctr[passes & 1] = 0;          // next used two passes from now
+            // every warp folds the tile partials in the same fixed order and updates its own copy of T:
+            // lane k + 9*part (part 0..2) adds column k over tiles = part (mod 3), in tile order
             double S[kNumSums];
+            {
+                double col = 0.0;
+                if (lane < 3 * kNumSums) {
+                    const int k = lane % kNumSums;
+                    for (int t = lane / kNumSums; t < ntiles; t += 3) col += redp[t * kNumSums + k];
+                }
 #pragma unroll
-            for (int k = 0; k < kNumSums; ++k) S[k] = 0.0;
-            for (int w = 0; w < nwarps; ++w) {
-#pragma unroll
-                for (int k = 0; k < kNumSums; ++k) S[k] += redp[w * kNumSums + k];
+                for (int k = 0; k < kNumSums; ++k)
+                    S[k] = (__shfl_sync(0xffffffffu, col, k) + __shfl_sync(0xffffffffu, col, k + kNumSums))
+                           + __shfl_sync(0xffffffffu, col, k + 2 * kNumSums);
             }
             {
-                const double n = (double)n1;
-                const double ma_x = S[0] / n, ma_y = S[1] / n, mb_x = S[2] / n, mb_y = S[3] / n;
+                double T[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
+                double cx, cy;
+                apply_T(T, s0.x, s0.y, cx, cy);
+                const double ma_x = S[0] * inv_n, ma_y = S[1] * inv_n, mb_x = S[2] * inv_n, mb_y = S[3] * inv_n;
                 // centred cross-covariance S = X Y^T (src/icp.py:29-32)
                 const double s00 = S[4] - S[0] * mb_x, s01 = S[5] - S[0] * mb_y;
                 const double s10 = S[6] - S[1] * mb_x, s11 = S[7] - S[1] * mb_y;
                 // rotation maximising tr(R S): closed form of the SVD + det fix (src/icp.py:33-38)
                 const double A = s00 + s11, Bv = s01 - s10;
-                const double h = hypot(A, Bv);
+                const double h2 = A * A + Bv * Bv;
                 double c = 1.0, s = 0.0;
-                if (h > 0.0) { c = A / h; s = Bv / h; }
+                if (h2 > 0.0 && h2 < 1e300) {
+                    const double rh = rsqrt(h2);
+                    c = A * rh; s = Bv * rh;
+                } else if (h2 > 0.0) {                                   // huge coordinates: scale first
+                    const double m = fmax(fabs(A), fabs(Bv));
+                    const double an = A / m, bn = Bv / m;
+                    const double rh = rsqrt(an * an + bn * bn);
+                    c = an * rh; s = bn * rh;
+                }
                 const double xbar = cx + ma_x, ybar = cy + ma_y;       // mean of moved source
                 const double qbx = g.x + mb_x, qby = g.y + mb_y;       // mean of matched target
                 double tx = qbx - (c * xbar - s * ybar);               // src/icp.py:39
@@ -434,14 +490,18 @@ icp_align_kernel(const KernelArgs a)
                 N[3] = s * T[0] + c * T[3];
                 N[4] = s * T[1] + c * T[4];
                 N[5] = s * T[2] + c * T[5] + ty;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) T[k] = N[k];
                 err = S[8];
-            }
-            if (tid == 0 && a.hist && passes < a.p.hist_cap) {
-                double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
+                __syncwarp();
+                if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) hrow[k] = T[k];
+                    for (int k = 0; k < 6; ++k) Tmine[k] = N[k];
+                    if (warp == 0 && a.hist && passes < a.p.hist_cap) {
+                        double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) hrow[k] = N[k];
+                    }
+                }
+                __syncwarp();
             }
             ++passes;
             // stop rules, in the reference's order (src/icp.py:86-95)
@@ -454,7 +514,7 @@ icp_align_kernel(const KernelArgs a)
         }
         if (tid == 0) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = T[k];
+            for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = Tmine[k];
             a.err_out[pid] = err;
             a.passes_out[pid] = passes;
         }
@@ -466,9 +526,9 @@ icp_align_kernel(const KernelArgs a)
         __syncthreads();        // smem is reused by the next problem
     }
     if (a.executed) {
-        // chunks processed by this warp x 16 targets x 128 source-point slots
-        executed = executed * (unsigned long long)(kChunk * 32 * R);
-        if (lane == 0 && executed) atomicAdd(a.executed, executed);
+        // chunks processed by this warp x 16 targets x 32*R source-point slots
+        const unsigned long long ex = (unsigned long long)executed * (unsigned long long)(kChunk * 32 * R);
+        if (lane == 0 && ex) atomicAdd(a.executed, ex);
     }
 }
 
