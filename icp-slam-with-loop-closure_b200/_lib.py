@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "libicpb.so")
+SO_PATH = os.environ.get("ICPB_SO") or os.path.join(_HERE, "libicpb.so")   # ICPB_SO: tuning builds
 
 FLAG_EXHAUSTIVE = 1
 

@@ -30,7 +30,10 @@ int fail(int code, const char *fmt, const char *detail = "")
         }                                                                                 \
     } while (0)
 
-constexpr int kPointsPerThread = 2;
+#ifndef ICPB_R
+#define ICPB_R 2
+#endif
+constexpr int kPointsPerThread = ICPB_R;
 constexpr int kQueueRing = 64;
 constexpr int kMaxSmem = 227 * 1024;
 

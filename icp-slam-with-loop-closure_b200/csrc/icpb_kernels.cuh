@@ -160,17 +160,60 @@ __device__ __forceinline__ void decode_pair(int64_t k, int64_t n, int32_t &i_out
     j_out = (int32_t)(k - start + i + 1);
 }
 
-__device__ __forceinline__ float warp_max(float v)
+// Warp-wide float max/min through the integer REDUX unit: one instruction instead of a 5-level
+// shuffle tree.  Floats are mapped to unsigned keys whose order equals the float order.
+__device__ __forceinline__ unsigned f2key(float f)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-__device__ __forceinline__ float warp_min(float v)
+__device__ __forceinline__ float key2f(unsigned k)
 {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ float warp_max(float v) { return key2f(__reduce_max_sync(0xffffffffu, f2key(v))); }
+__device__ __forceinline__ float warp_min(float v) { return key2f(__reduce_min_sync(0xffffffffu, f2key(v))); }
+// non-negative inputs: the bit pattern is already ordered
+__device__ __forceinline__ float warp_max_nonneg(float v)
+{
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+}
+
+// Butterfly reduction of 8 doubles across the warp: each level halves the number of values a lane
+// carries (lanes exchange the half they do not keep), then two plain levels finish.  9 double
+// shuffles instead of 40.  Afterwards lane L holds the warp total of value
+// id = 4*bit4(L) + 2*bit3(L) + bit2(L).  The addition order is fixed, so the result is
+// deterministic.
+__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
+{
+    double w4[4], w2[2], w1;
+    {
+        const bool up = lane & 16;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+        for (int j = 0; j < 4; ++j) {
+            const double send = up ? v[j] : v[j + 4];
+            const double keep = up ? v[j + 4] : v[j];
+            w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double send = up ? w4[j] : w4[j + 2];
+            const double keep = up ? w4[j + 2] : w4[j];
+            w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+        const double send = up ? w2[0] : w2[1];
+        const double keep = up ? w2[1] : w2[0];
+        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    return w1;
 }
 
 // PRUNE = false: exhaustive sweep over every chunk (the reference's brute force; used for the
@@ -181,7 +224,10 @@ __device__ __forceinline__ float warp_min(float v)
 // shared counter (tiles differ in how many chunks survive pruning); partial sums are stored per
 // tile and folded in tile order, so the result does not depend on which warp ran which tile.
 template <int R, bool PRUNE>
-__global__ void __launch_bounds__(256, 3)
+#ifndef ICPB_MIN_CTAS
+#define ICPB_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, ICPB_MIN_CTAS)
 icp_align_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -243,7 +289,7 @@ icp_align_kernel(const KernelArgs a)
                 }
                 tqx[j] = x; tqy[j] = y;
             }
-            qm = warp_max(qm);
+            qm = warp_max_nonneg(qm);
             if (lane == 0) atomicMax(&s_qmax_bits, __float_as_uint(qm));   // qm >= 0: bit order = value order
         }
         if (lane < 6) {
@@ -299,31 +345,63 @@ icp_align_kernel(const KernelArgs a)
                         px[r] = (float)X; py[r] = (float)Y;
                     }
                 }
+                float tcx = 0.f, tcy = 0.f, reach = kInf;
                 if (PRUNE) {
+                    // bounding circle of the tile's points
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        float ub = kInf;
-                        if (passes > 0) {
-                            const int j = corr_s[min(i0 + r, n1 - 1)];   // previous pass's match: a real target
-                            ub = dist32(px[r], py[r], tqx[j], tqy[j]);
-                        } else {
-                            for (int c = 0; c < nchunks; ++c)    // first pass: every 16th target
-                                ub = fminf(ub, dist32(px[r], py[r], tqx[c * kChunk], tqy[c * kChunk]));
-                        }
-                        ubmax = fmaxf(ubmax, ub + filter_tol(ub, px[r], py[r], qmax));
                         lx = fminf(lx, px[r]); hx = fmaxf(hx, px[r]);
                         ly = fminf(ly, py[r]); hy = fmaxf(hy, py[r]);
                     }
-                }
-                float tcx = 0.f, tcy = 0.f, reach = kInf;
-                if (PRUNE) {
                     lx = warp_min(lx); ly = warp_min(ly); hx = warp_max(hx); hy = warp_max(hy);
                     tcx = 0.5f * (lx + hx); tcy = 0.5f * (ly + hy);
                     float rho2 = 0.0f;
 #pragma unroll
                     for (int r = 0; r < R; ++r) rho2 = fmaxf(rho2, dist32(tcx, tcy, px[r], py[r]));
-                    rho2 = warp_max(rho2);
-                    ubmax = warp_max(ubmax);
+                    rho2 = warp_max_nonneg(rho2);
+                    // upper bound of every point's nearest-neighbour filter distance: its distance to
+                    // a real target -- the previous pass's match, or on the first pass the best
+                    // target in the chunks around the chunk centre nearest to the tile centre
+                    float ub[R];
+                    if (passes > 0) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int j = corr_s[min(i0 + r, n1 - 1)];
+                            ub[r] = dist32(px[r], py[r], tqx[j], tqy[j]);
+                        }
+                    } else {
+                        unsigned key = 0xffffffffu;
+                        for (int c = lane; c < nchunks; c += 32) {
+                            const float4 bc = cb[c];
+                            const unsigned k = (__float_as_uint(dist32(tcx, tcy, bc.x, bc.y)) & 0xfffff000u) | (unsigned)min(c, 4095);
+                            key = min(key, k);
+                        }
+                        const int cstar = (int)(__reduce_min_sync(0xffffffffu, key) & 0xfffu);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) ub[r] = kInf;
+                        const float4 *qx4 = reinterpret_cast<const float4 *>(tqx);
+                        const float4 *qy4 = reinterpret_cast<const float4 *>(tqy);
+                        for (int c = max(cstar - 1, 0); c <= min(cstar + 1, nchunks - 1); ++c) {
+                            float4 X[4], Y[4];
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                float d[16];
+                                const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
+                                float cm = min3f(d[0], d[1], d[2]);
+                                cm = min3f(cm, d[3], d[4]);   cm = min3f(cm, d[5], d[6]);
+                                cm = min3f(cm, d[7], d[8]);   cm = min3f(cm, d[9], d[10]);
+                                cm = min3f(cm, d[11], d[12]); cm = min3f(cm, d[13], d[14]);
+                                ub[r] = fminf(ub[r], fminf(cm, d[15]));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) ubmax = fmaxf(ubmax, ub[r] + filter_tol(ub[r], px[r], py[r], qmax));
+                    ubmax = warp_max_nonneg(ubmax);
                     // every target within sqrt(ubmax) of some point of the tile lies within `reach`
                     // of the tile centre; e covers the fp32 rounding of the centres and differences
                     const float e = 4.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))) + qmax);
@@ -430,11 +508,13 @@ icp_align_kernel(const KernelArgs a)
                         }
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < kNumSums; ++k) redp[tile * kNumSums + k] = sum[k];
+                {
+                    const double (&s8)[8] = reinterpret_cast<const double (&)[8]>(sum);
+                    const double tot = warp_sum8(s8, lane);                // sums 0..7, see warp_sum8
+                    const double e8 = warp_sum(sum[8]);
+                    if ((lane & 3) == 0)
+                        redp[tile * kNumSums + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
+                    if (lane == 1) redp[tile * kNumSums + 8] = e8;
                 }
             }
 
