@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 #include <vector>
@@ -87,7 +88,7 @@ struct icpb_ctx {
 
 namespace {
 
-int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c, kernel_fn fn)
+int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn)
 {
     if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
     const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
@@ -101,7 +102,15 @@ int make_cfg(icpb_ctx *h, int64_t longest, LaunchCfg *c, kernel_fn fn)
         return ICPB_ETOOLONG;
     }
     int threads = (int)(ntile * 32);                      // one warp per tile, up to 8 warps
-    if (threads > 256) threads = 256;
+    // Small CTAs keep more independent problems in flight per SM (less idling at the per-pass
+    // barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
+    // problems per resident CTA (tail) or a single pair (latency).
+    int max_threads = (B >= 2048) ? 128 : 256;
+    if (const char *t = getenv("ICPB_THREADS")) {         // tuning experiments only
+        const int v = atoi(t);
+        if (v >= 32 && v <= 256 && v % 32 == 0) max_threads = v;
+    }
+    if (threads > max_threads) threads = max_threads;
     if (threads < 32) threads = 32;
     c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
     c->nchunk_cap = (int)nchunk; c->ntile_cap = (int)ntile;
@@ -138,7 +147,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     if (B == 0) return 0;
     LaunchCfg cfg;
     kernel_fn fn = pick_kernel(p);
-    int rc = make_cfg(h, longest, &cfg, fn);
+    int rc = make_cfg(h, longest, B, &cfg, fn);
     if (rc) return rc;
     icpb::KernelArgs a;
     a.xy = xy; a.offsets = offsets; a.pairs = d_pairs; a.init = d_init; a.B = B; a.n_scans = n_scans;
@@ -383,7 +392,7 @@ int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out)
     CU(cudaSetDevice(h->device));
     LaunchCfg cfg;
     kernel_fn fn = pick_kernel(nullptr);
-    int rc = make_cfg(h, h->longest, &cfg, fn);
+    int rc = make_cfg(h, h->longest, B > 0 ? B : (int64_t)1 << 40, &cfg, fn);
     if (rc) return rc;
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, fn));

@@ -108,6 +108,14 @@ __device__ __forceinline__ float min3f(float a, float b, float c)
     return fminf(fminf(a, b), c);
 }
 
+// MUFU square root (1-2 ulp); every use below carries a much larger safety factor
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Bound on |fp32 filter distance - exact distance| doubled, as a function of the best filter
 // distance m1.  e bounds the error of one coordinate difference: both inputs were rounded to
 // fp32 (relative 2^-24 each) and the subtraction rounds once more.
@@ -115,7 +123,7 @@ __device__ __forceinline__ float filter_tol(float m1, float px, float py, float 
 {
     const float u = 5.9604645e-8f;                              // 2^-24
     const float e = 2.0f * u * (fmaxf(fabsf(px), fabsf(py)) + qmax) * 1.0001f;
-    return 8.0f * sqrtf(m1) * e + 16.0f * e * e + 16.0f * u * m1;
+    return 8.0f * sqrt_fast(m1) * e + 16.0f * e * e + 16.0f * u * m1;
 }
 
 // Rare path of the decision step: all targets j in [lo, hi) whose filter distance is <= thr are
@@ -400,12 +408,16 @@ icp_align_kernel(const KernelArgs a)
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < R; ++r) ubmax = fmaxf(ubmax, ub[r] + filter_tol(ub[r], px[r], py[r], qmax));
+                    for (int r = 0; r < R; ++r) ubmax = fmaxf(ubmax, ub[r]);
                     ubmax = warp_max_nonneg(ubmax);
+                    // the decision threshold of any point of the tile is at most ubmax + tol(ubmax)
+                    // (filter_tol grows with the distance and with the coordinate magnitudes)
+                    const float pmax = fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy)));
+                    ubmax += filter_tol(ubmax, pmax, pmax, qmax);
                     // every target within sqrt(ubmax) of some point of the tile lies within `reach`
                     // of the tile centre; e covers the fp32 rounding of the centres and differences
-                    const float e = 4.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))) + qmax);
-                    reach = (sqrtf(rho2) + sqrtf(ubmax)) * 1.00001f + e;
+                    const float e = 4.0f * 1.1920929e-7f * (pmax + qmax);
+                    reach = (sqrt_fast(rho2) + sqrt_fast(ubmax)) * 1.0001f + e;
                 }
 
                 float m1[R], m2[R];
@@ -484,14 +496,11 @@ icp_align_kernel(const KernelArgs a)
 #pragma unroll
                                 for (int v = 0; v < 4; ++v) dist32x4(PX, PY, bx[v], by[v], d + 4 * v);
                             }
-                            int cnt = 0, pos = 0;
+                            int cntpos = 0;                      // candidates * 256 + sum of their positions
 #pragma unroll
-                            for (int k = 0; k < kChunk; ++k) {
-                                const bool in = d[k] <= thr;
-                                cnt += in ? 1 : 0;
-                                pos += in ? k : 0;
-                            }
-                            int idx = j0 + pos;                  // unique candidate: no fp64 needed
+                            for (int k = 0; k < kChunk; ++k) cntpos += (d[k] <= thr) ? (256 + k) : 0;
+                            const int cnt = cntpos >> 8;
+                            int idx = j0 + (cntpos & 255);       // unique candidate: no fp64 needed
                             if (m2[r] <= thr)                    // another chunk is within the bound
                                 idx = exact_decide(0, n2, j0, thr, px[r], py[r], Px, Py, tqx, tqy, dst);
                             else if (cnt != 1)
