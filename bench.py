@@ -12,8 +12,9 @@ whole 4,999-pair batch.  With N GPUs every rank aligns its own 4,999-pair chain 
 and an NCCL all-gather returns every pair's constraint record to all ranks.
 
 `value`     device-timed: scan table, pairs and initial guesses already resident in HBM.
-`e2e`       the same step through the public host API (IcpEngine.set_scans + run, i.e. the C
-            ABI's icpb_upload_scans + icpb_run_host): pinned host buffers in, results out.
+`e2e`       the same step through the public host API (IcpEngine.align = the C ABI's
+            icpb_align_host: segmented upload overlapped with the kernels): pinned host buffers in,
+            results out in host memory.
 `roofline`  FP32-pipe roofline of the alignment kernel: algorithmic
             point-pair distance evaluations (sum over pairs of passes*N1*N2) per second against
             SMs * 128 lanes * f_max / 4 instruction slots.
@@ -34,6 +35,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 4,999-pair chain, from the
+# committed `ncu --set full` capture (profiles/r01h_align_ncu_full_summary.csv); None until measured
+TRAFFIC_NCU = 88.9e6   # 81.3 MB read (= one pass over the 81 MB scan table) + 7.6 MB written
 METRIC = "icp_scan_pair_alignments_per_sec"
 UNIT = "pairs/s"
 SEED = 467002
@@ -268,6 +272,20 @@ def main():
     lens = table.lengths
     work = float(np.sum(passes * lens[pairs[:, 0]] * lens[pairs[:, 1]]))          # PDE per step on this rank
     info = eng.kernel_info(B)
+    # the same kernel with pruning switched off (every source point sweeps every target, the
+    # reference's brute force): this is the variant the FP32-pipe roofline is defined for
+    ex_ms = []
+    for k in range(2 + min(args.steps, 5)):
+        flush.fill_(float(k))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100, exhaustive=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= 2:
+            ex_ms.append(e0.elapsed_time(e1))
+    assert np.array_equal(out_pass.cpu().numpy().astype(np.int64), passes)
+    ex_s = float(np.mean(ex_ms)) * 1e-3
     # one instrumented launch (outside every timed region): distance evaluations actually executed
     eng.count_work(True)
     eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
@@ -282,8 +300,8 @@ def main():
         eng2 = gicp.IcpEngine(local)
 
         def step_host():
-            eng2.set_scans(tab_pin)
-            return eng2.run(pairs_h, init_h, epsilon=0.05, max_iters=100)
+            # the public call: scans + pairs + initial guesses in host memory -> constraints in host memory
+            return eng2.align(tab_pin, pairs_h, init_h, epsilon=0.05, max_iters=100)
 
         for _ in range(max(args.warmup, 1)):
             res = step_host()
@@ -322,7 +340,13 @@ def main():
         alg_bytes = float(np.sum(16.0 * (lens[pairs[:, 0]] + lens[pairs[:, 1]]) + 60.0 + 56.0))
         roofline = {
             "bound": "fp32_pipe", "achieved": achieved * 1e-12, "peak": pde_peak * 1e-12, "unit": "TPDE/s",
-            "frac": achieved / pde_peak, "traffic": None,
+            "frac": achieved / pde_peak, "traffic": TRAFFIC_NCU,
+            "note": "achieved counts ALGORITHMIC distance evaluations (passes*N1*N2); the product kernel "
+                    "proves most of them unnecessary (exact chunk pruning) and executes only "
+                    "executed_share of them, so frac can exceed 1; `exhaustive` is the same kernel "
+                    "with pruning off, the variant the pipe roofline bounds",
+            "exhaustive": {"kernel_ms": ex_s * 1e3, "achieved": work / ex_s * 1e-12, "frac": work / ex_s / pde_peak,
+                           "pairs_per_s": B / ex_s},
             "definition": "PDE = one point-pair distance evaluation = 4 FP32-pipe lane-slots (FADD,FADD,FMUL,FFMA); "
                           "peak = SMs*128*sm_max_mhz/4 (SURVEY.md 8d formula; clock " + peak_src + ")",
             "pde_per_launch": work, "kernel_ms": kern_s * 1e3,

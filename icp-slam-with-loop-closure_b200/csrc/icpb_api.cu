@@ -83,6 +83,9 @@ struct icpb_ctx {
     // scratch for host-pointer entry points
     DevBuf s_pairs, s_init, s_T, s_err, s_passes, s_hist, s_corr, s_pair_xy, s_pair_off;
     cudaStream_t stream = nullptr;
+    cudaStream_t cstream[2] = {nullptr, nullptr};   // compute streams of the pipelined host entry point
+    cudaEvent_t seg_ev[16] = {};                    // "scan segment k has arrived"
+    cudaEvent_t done_ev[2] = {};
     int max_smem_set = 0;
 };
 
@@ -142,12 +145,12 @@ int check_params(const icpb_params *p, int64_t B)
 int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scans, int64_t longest,
            const int32_t *d_pairs, const double *d_init, int64_t B, const icpb_params *p,
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
-           cudaStream_t stream)
+           cudaStream_t stream, int64_t B_total = 0)
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
     kernel_fn fn = pick_kernel(p);
-    int rc = make_cfg(h, longest, B, &cfg, fn);
+    int rc = make_cfg(h, longest, B_total > B ? B_total : B, &cfg, fn);
     if (rc) return rc;
     icpb::KernelArgs a;
     a.xy = xy; a.offsets = offsets; a.pairs = d_pairs; a.init = d_init; a.B = B; a.n_scans = n_scans;
@@ -206,6 +209,9 @@ int icpb_create(int device, icpb_handle *out)
     cudaError_t e = cudaMalloc(&h->queue, sizeof(unsigned long long) * (kQueueRing + 1));
     if (e == cudaSuccess) e = cudaMemset(h->queue, 0, sizeof(unsigned long long) * (kQueueRing + 1));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&h->cstream[k], cudaStreamNonBlocking);
+    for (int k = 0; k < 16 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->seg_ev[k], cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->done_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "icpb_create: %s", cudaGetErrorString(e));
         if (h->queue) cudaFree(h->queue);
@@ -221,6 +227,9 @@ int icpb_destroy(icpb_handle h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (int k = 0; k < 2; ++k) if (h->cstream[k]) { cudaStreamSynchronize(h->cstream[k]); cudaStreamDestroy(h->cstream[k]); }
+    for (int k = 0; k < 16; ++k) if (h->seg_ev[k]) cudaEventDestroy(h->seg_ev[k]);
+    for (int k = 0; k < 2; ++k) if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -352,6 +361,123 @@ int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, i
     CU(cudaSetDevice(h->device));
     return run_host_common(h, h->xy, h->offsets, h->n_scans, h->longest, h_pairs, h_init, B, p,
                            h_T, h_err, h_passes, h_hist, h_corr);
+}
+
+/* Upload + align with the upload hidden behind the kernels: the scan table goes up in segments on
+ * the copy stream; pairs are grouped by the segment that completes them (the larger of their two
+ * scan ids) and every group is launched as soon as its segment has arrived. */
+int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                    const int32_t *h_pairs, const double *h_init, int64_t B, const icpb_params *p,
+                    double *h_T, double *h_err, int32_t *h_passes)
+{
+    if (!h || !h_xy || !h_offsets || n_scans <= 0) return fail(ICPB_EINVAL, "icpb_align_host: bad argument%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if (p->pair_mode != 0 || p->hist_cap > 0 || p->corr_stride > 0)
+        return fail(ICPB_EINVAL, "icpb_align_host: explicit pairs, no history/correspondences (use upload + run)%s");
+    int64_t longest = 0;
+    if ((rc = validate_offsets(h_offsets, n_scans, &longest))) return rc;
+    if (B > 0 && (!h_pairs || !h_T || !h_err || !h_passes)) return fail(ICPB_EINVAL, "null pointer%s");
+    for (int64_t b = 0; b < 2 * B; ++b)
+        if (h_pairs[b] < 0 || h_pairs[b] >= n_scans) return fail(ICPB_EINVAL, "pair index out of range%s");
+    CU(cudaSetDevice(h->device));
+    const size_t nb_xy = sizeof(double) * 2 * (size_t)h_offsets[n_scans];
+    const size_t nb_off = sizeof(int64_t) * (size_t)(n_scans + 1);
+    if ((rc = h->own_xy.reserve(nb_xy))) return rc;
+    if ((rc = h->own_off.reserve(nb_off))) return rc;
+    h->xy = (const double *)h->own_xy.p; h->offsets = (const int64_t *)h->own_off.p;
+    h->n_scans = n_scans; h->longest = longest;
+    if (B == 0) {
+        CU(cudaMemcpyAsync(h->own_xy.p, h_xy, nb_xy, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    // segments of roughly equal size: enough of them that the first kernels start early, few
+    // enough that every group still fills the GPU (a group of a few hundred pairs would not)
+    int nseg = (int)(nb_xy / (16u << 20)) + 1;
+    if (nseg > 4) nseg = 4;                                  // measured best on the 81 MB / 4,999-pair chain
+    if (const char *t = getenv("ICPB_SEGMENTS")) {          // tuning experiments only
+        const int v = atoi(t);
+        if (v >= 1 && v <= 16) nseg = v;
+    }
+    if (nseg > n_scans) nseg = (int)n_scans;
+    std::vector<int64_t> seg_end(nseg);                       // exclusive scan id
+    {
+        const int64_t total = h_offsets[n_scans];
+        int64_t s = 0;
+        for (int k = 0; k < nseg; ++k) {
+            const int64_t want = total * (k + 1) / nseg;
+            while (s < n_scans && h_offsets[s] < want) ++s;
+            if (k == nseg - 1) s = n_scans;
+            seg_end[k] = s > 0 ? s : 1;
+        }
+    }
+    // group pairs by completing segment (stable counting sort)
+    std::vector<int32_t> seg_of_scan((size_t)n_scans);
+    for (int64_t s = 0, k = 0; s < n_scans; ++s) { while (s >= seg_end[k]) ++k; seg_of_scan[s] = (int32_t)k; }
+    std::vector<int64_t> start(nseg + 1, 0);
+    std::vector<int32_t> seg_of_pair((size_t)B);
+    for (int64_t b = 0; b < B; ++b) {
+        const int32_t m = h_pairs[2 * b] > h_pairs[2 * b + 1] ? h_pairs[2 * b] : h_pairs[2 * b + 1];
+        seg_of_pair[b] = seg_of_scan[m];
+        ++start[seg_of_pair[b] + 1];
+    }
+    for (int k = 0; k < nseg; ++k) start[k + 1] += start[k];
+    std::vector<int64_t> perm((size_t)B), fill(start.begin(), start.end() - 1);
+    for (int64_t b = 0; b < B; ++b) perm[fill[seg_of_pair[b]]++] = b;
+    std::vector<int32_t> ppairs((size_t)(2 * B));
+    std::vector<double> pinit(h_init ? (size_t)(6 * B) : 0);
+    for (int64_t q = 0; q < B; ++q) {
+        const int64_t b = perm[q];
+        ppairs[2 * q] = h_pairs[2 * b]; ppairs[2 * q + 1] = h_pairs[2 * b + 1];
+        if (h_init) memcpy(&pinit[6 * q], h_init + 6 * b, 6 * sizeof(double));
+    }
+    const size_t nbP = sizeof(int32_t) * 2 * (size_t)B, nbI = sizeof(double) * 6 * (size_t)B;
+    if ((rc = h->s_pairs.reserve(nbP))) return rc;
+    if (h_init && (rc = h->s_init.reserve(nbI))) return rc;
+    if ((rc = h->s_T.reserve(nbI))) return rc;
+    if ((rc = h->s_err.reserve(sizeof(double) * (size_t)B))) return rc;
+    if ((rc = h->s_passes.reserve(sizeof(int32_t) * (size_t)B))) return rc;
+    cudaStream_t cp = h->stream;
+    CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
+    CU(cudaMemcpyAsync(h->s_pairs.p, ppairs.data(), nbP, cudaMemcpyHostToDevice, cp));
+    if (h_init) CU(cudaMemcpyAsync(h->s_init.p, pinit.data(), nbI, cudaMemcpyHostToDevice, cp));
+    int64_t s_prev = 0;
+    for (int k = 0; k < nseg; ++k) {
+        const int64_t o0 = h_offsets[s_prev], o1 = h_offsets[seg_end[k]];
+        if (o1 > o0)
+            CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
+                               cudaMemcpyHostToDevice, cp));
+        CU(cudaEventRecord(h->seg_ev[k], cp));
+        s_prev = seg_end[k];
+        const int64_t b0 = start[k], nb = start[k + 1] - start[k];
+        if (nb == 0) continue;
+        cudaStream_t cs = h->cstream[k & 1];
+        CU(cudaStreamWaitEvent(cs, h->seg_ev[k], 0));
+        rc = launch(h, h->xy, h->offsets, n_scans, longest, (const int32_t *)h->s_pairs.p + 2 * b0,
+                    h_init ? (const double *)h->s_init.p + 6 * b0 : nullptr, nb, p,
+                    (double *)h->s_T.p + 6 * b0, (double *)h->s_err.p + b0, (int32_t *)h->s_passes.p + b0,
+                    nullptr, nullptr, cs, B);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaEventRecord(h->done_ev[k], h->cstream[k]));
+        CU(cudaStreamWaitEvent(cp, h->done_ev[k], 0));
+    }
+    std::vector<double> tT((size_t)(6 * B)), tE((size_t)B);
+    std::vector<int32_t> tP((size_t)B);
+    CU(cudaMemcpyAsync(tT.data(), h->s_T.p, nbI, cudaMemcpyDeviceToHost, cp));
+    CU(cudaMemcpyAsync(tE.data(), h->s_err.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, cp));
+    CU(cudaMemcpyAsync(tP.data(), h->s_passes.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, cp));
+    CU(cudaStreamSynchronize(cp));
+    for (int64_t q = 0; q < B; ++q) {
+        const int64_t b = perm[q];
+        memcpy(h_T + 6 * b, &tT[6 * q], 6 * sizeof(double));
+        h_err[b] = tE[q];
+        h_passes[b] = tP[q];
+    }
+    return 0;
 }
 
 int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,

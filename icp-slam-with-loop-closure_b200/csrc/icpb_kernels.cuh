@@ -497,8 +497,15 @@ icp_align_kernel(const KernelArgs a)
                                 for (int v = 0; v < 4; ++v) dist32x4(PX, PY, bx[v], by[v], d + 4 * v);
                             }
                             int cntpos = 0;                      // candidates * 256 + sum of their positions
-#pragma unroll
-                            for (int k = 0; k < kChunk; ++k) cntpos += (d[k] <= thr) ? (256 + k) : 0;
+                            // one FSETP + one predicated IADD per target
+#define ICPB_CAND(K) asm("{ .reg .pred q; setp.le.f32 q, %1, %2; @q add.s32 %0, %0, %3; }" \
+                         : "+r"(cntpos) : "f"(d[K]), "f"(thr), "n"(256 + K))
+                            ICPB_CAND(0);  ICPB_CAND(1);  ICPB_CAND(2);  ICPB_CAND(3);
+                            ICPB_CAND(4);  ICPB_CAND(5);  ICPB_CAND(6);  ICPB_CAND(7);
+                            ICPB_CAND(8);  ICPB_CAND(9);  ICPB_CAND(10); ICPB_CAND(11);
+                            ICPB_CAND(12); ICPB_CAND(13); ICPB_CAND(14); ICPB_CAND(15);
+#undef ICPB_CAND
+                            static_assert(kChunk == 16, "candidate count is written out for 16 targets");
                             const int cnt = cntpos >> 8;
                             int idx = j0 + (cntpos & 255);       // unique candidate: no fp64 needed
                             if (m2[r] <= thr)                    // another chunk is within the bound

@@ -228,6 +228,38 @@ class IcpEngine:
             history[pad] = np.eye(3)
         return BatchResult(_to33(T6), err, passes, history, corr)
 
+    # -- upload + run in one call, upload overlapped with the kernels ---------------------------
+    def align(self, scans, pairs, init_transforms=None, epsilon=0.01, max_iters=100, stopping_thresh=0.0001,
+              rotation_only=False, exhaustive: bool = False) -> BatchResult:
+        """`set_scans` + `run` through icpb_align_host: the scan table is copied in segments and
+        every pair starts as soon as both of its scans are on the device."""
+        table = scans if isinstance(scans, ScanTable) else ScanTable(scans)
+        p = _params(epsilon, max_iters, stopping_thresh, rotation_only, exhaustive)
+        pairs_a = np.ascontiguousarray(pairs, dtype=np.int32)
+        if pairs_a.size == 0:
+            pairs_a = pairs_a.reshape(0, 2)
+        if pairs_a.ndim != 2 or pairs_a.shape[1] != 2:
+            raise ValueError(f"pairs has shape {pairs_a.shape}; expected (B, 2) of (source, target) scan ids")
+        if pairs_a.size and (pairs_a.min() < 0 or pairs_a.max() >= table.n_scans):
+            raise ValueError("pair index out of range")
+        B = len(pairs_a)
+        p.k_block = max(B, 1)
+        init6 = None
+        if init_transforms is not None:
+            it = np.asarray(init_transforms, dtype=np.float64)
+            if it.shape != (B, 3, 3):
+                raise ValueError(f"init_transforms has shape {it.shape}; expected ({B}, 3, 3)")
+            init6 = _to6(it)
+        T6 = np.empty((B, 6))
+        err = np.empty(B)
+        passes = np.empty(B, dtype=np.int32)
+        _lib.check(self._L.icpb_align_host(self._h, _ptr(table.xy), _ptr(table.offsets), table.n_scans,
+                                           _ptr(pairs_a), _ptr(init6), B, ctypes.byref(p),
+                                           _ptr(T6), _ptr(err), _ptr(passes)), "icpb_align_host")
+        self.table = table
+        self._keep = None
+        return BatchResult(_to33(T6), err, passes, None, None)
+
     # -- device-buffer run (inputs and outputs resident in HBM; torch tensors) ---------------
     def run_device(self, pairs_t, init_t, out_T, out_err, out_passes, epsilon=0.01, max_iters=100,
                    stopping_thresh=0.0001, rotation_only=False, all_pairs: tuple | None = None,
@@ -385,7 +417,11 @@ def icp_batch(scans, pairs, init_transforms=None, epsilon=0.01, max_iters=100, s
     for every pair.
     """
     e = engine(device)
-    if not (isinstance(scans, ScanTable) and e.table is scans):
-        e.set_scans(scans)
+    if isinstance(scans, ScanTable) and e.table is scans:          # already resident
+        return e.run(pairs, init_transforms, epsilon, max_iters, stopping_thresh, rotation_only,
+                     return_history, return_correspondences)
+    if not (return_history or return_correspondences):
+        return e.align(scans, pairs, init_transforms, epsilon, max_iters, stopping_thresh, rotation_only)
+    e.set_scans(scans)
     return e.run(pairs, init_transforms, epsilon, max_iters, stopping_thresh, rotation_only,
                  return_history, return_correspondences)

@@ -105,6 +105,16 @@ int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, i
                   const icpb_params *p, double *h_T, double *h_err, int32_t *h_passes,
                   double *h_hist, int32_t *h_corr);
 
+/* icpb_upload_scans + icpb_run_host in one call with the upload overlapped with the kernels: the
+ * scan table is copied in segments and every pair is launched as soon as both of its scans have
+ * arrived.  Explicit pairs only, no history / correspondences.  This is what the Python
+ * `icp_batch(scans, pairs, ...)` calls: the replacement of the whole
+ * `Parallel(...)(delayed(icp.icp)(np.c_[scan_i, 1], np.c_[scan_j, 1], ...) ...)` expression
+ * (scripts/main.py:240-247), argument pickling included. */
+int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                    const int32_t *h_pairs, const double *h_init, int64_t B, const icpb_params *p,
+                    double *h_T, double *h_err, int32_t *h_passes);
+
 /* One pair given directly as two (n, 2) float64 host arrays: the reference's
  * icp(pc1, pc2, init_transform, epsilon, max_iters, stopping_thresh, rotation_only)
  * (src/icp.py:72) and, with epsilon = +inf (one pass), icp_iteration() (src/icp.py:55-69). */

@@ -282,3 +282,28 @@ def test_pruning_on_unordered_clouds(gicp, c_oracle):
     np.testing.assert_array_equal(res.correspondences[0, :650], corr)
     dt, dth = pose_diff(res.T[0], T)
     assert dt < POSE_TOL and dth < POSE_TOL
+
+
+def test_pipelined_align_equals_upload_then_run(gicp):
+    """icpb_align_host (segmented upload overlapped with the kernels, pairs regrouped by segment)
+    returns exactly what upload + run returns, in the caller's pair order."""
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(8)
+    poses = synth.loop_trajectory(300, step=0.1)
+    scans = synth.scans_from_poses(poses, 720, rng, drop_frac=0.05)      # ~3.4 MB... several segments at 4 MB? no
+    scans = scans * 3                                                     # 900 scans, ~10 MB -> 3 segments
+    n = len(scans)
+    pairs = np.stack((rng.integers(0, n, 500), rng.integers(0, n, 500)), axis=1).astype(np.int32)
+    th = rng.uniform(-0.05, 0.05, 500)
+    init = np.stack([synth.pose_to_mat([0.02, -0.01, t]) for t in th])
+    e = gicp.IcpEngine()
+    a = e.align(scans, pairs, init, epsilon=0.05, max_iters=25)
+    e.set_scans(scans)
+    b = e.run(pairs, init, epsilon=0.05, max_iters=25)
+    np.testing.assert_array_equal(a.T, b.T)
+    np.testing.assert_array_equal(a.error, b.error)
+    np.testing.assert_array_equal(a.iters, b.iters)
+    c = e.align(scans, pairs, None, epsilon=0.05, max_iters=5)
+    d = e.run(pairs, None, epsilon=0.05, max_iters=5)
+    np.testing.assert_array_equal(c.T, d.T)
+    e.close()
