@@ -194,6 +194,11 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout at communicator creation; keep stdout for the one
+    # JSON line by pointing fd 1 at stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -376,7 +381,10 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
