@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
 EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destroy",
            "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
-           "icpb_count_work", "icpb_read_work", "icpb_align_host"]
+           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
     L.icpb_run_device.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p, vp]
     L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_align_host.argtypes = [vp, dp, vp, i64, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p]
+    L.icpb_fit_pairs_host.argtypes = [vp, dp, dp, i64, dp, dp]
     L.icpb_icp_pair_host.argtypes = [vp, dp, i64, dp, i64, dp, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_get_kernel_info.argtypes = [vp, i64, ctypes.POINTER(IcpbKernelInfo)]
     L.icpb_launch_count.argtypes = [vp]

@@ -511,6 +511,30 @@ int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,
                            pair, h_init6, 1, &q, h_T6, h_err, h_passes, h_hist, h_corr);
 }
 
+int icpb_fit_pairs_host(icpb_handle h, const double *h_a_xy, const double *h_b_xy, int64_t n,
+                        double *h_T6, double *h_err)
+{
+    if (!h || !h_a_xy || !h_b_xy || n <= 0 || n > 0x7fffffff || !h_T6 || !h_err)
+        return fail(ICPB_EINVAL, "icpb_fit_pairs_host: bad argument%s");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    const size_t nb = sizeof(double) * 2 * (size_t)n;
+    if ((rc = h->s_pair_xy.reserve(2 * nb))) return rc;
+    if ((rc = h->s_T.reserve(sizeof(double) * 8))) return rc;
+    double *da = (double *)h->s_pair_xy.p, *db = da + 2 * n;
+    CU(cudaMemcpyAsync(da, h_a_xy, nb, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(db, h_b_xy, nb, cudaMemcpyHostToDevice, h->stream));
+    icpb::fit_pairs_kernel<<<1, 256, 0, h->stream>>>((const double2 *)da, (const double2 *)db, (int)n,
+                                                     (double *)h->s_T.p, (double *)h->s_T.p + 6);
+    CU(cudaGetLastError());
+    double out[7];
+    CU(cudaMemcpyAsync(out, h->s_T.p, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(h_T6, out, 6 * sizeof(double));
+    *h_err = out[6];
+    return 0;
+}
+
 int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out)
 {
     if (!h || !out) return fail(ICPB_EINVAL, "icpb_get_kernel_info: bad argument%s");

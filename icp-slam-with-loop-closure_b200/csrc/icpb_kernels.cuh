@@ -628,4 +628,53 @@ icp_align_kernel(const KernelArgs a)
     }
 }
 
+
+// Rigid fit of n matched point pairs a[i] -> b[i] and their SSE: the reference's get_transform
+// (src/icp.py:22-46) and get_error (src/icp.py:49-52) as stand-alone operations.  One CTA.
+__global__ void __launch_bounds__(256)
+fit_pairs_kernel(const double2 *a, const double2 *b, int n, double *T_out, double *err_out)
+{
+    __shared__ double red[8][kNumSums];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2 a0 = a[0], b0 = b[0];
+    double sum[kNumSums];
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double2 p = a[i], q = b[i];
+        const double ax = p.x - a0.x, ay = p.y - a0.y, bx = q.x - b0.x, by = q.y - b0.y;
+        sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
+        sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
+        sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
+        const double ex = p.x - q.x, ey = p.y - q.y;
+        sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+    }
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNumSums; ++k) red[warp][k] = sum[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double S[kNumSums];
+        for (int k = 0; k < kNumSums; ++k) {
+            S[k] = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) S[k] += red[w][k];
+        }
+        const double inv_n = 1.0 / (double)n;
+        const double ma_x = S[0] * inv_n, ma_y = S[1] * inv_n, mb_x = S[2] * inv_n, mb_y = S[3] * inv_n;
+        const double s00 = S[4] - S[0] * mb_x, s01 = S[5] - S[0] * mb_y;
+        const double s10 = S[6] - S[1] * mb_x, s11 = S[7] - S[1] * mb_y;
+        const double A = s00 + s11, Bv = s01 - s10;
+        const double h = hypot(A, Bv);
+        double c = 1.0, s = 0.0;
+        if (h > 0.0) { c = A / h; s = Bv / h; }
+        const double xbar = a0.x + ma_x, ybar = a0.y + ma_y, qbx = b0.x + mb_x, qby = b0.y + mb_y;
+        T_out[0] = c; T_out[1] = -s; T_out[2] = qbx - (c * xbar - s * ybar);
+        T_out[3] = s; T_out[4] = c;  T_out[5] = qby - (s * xbar + c * ybar);
+        *err_out = S[8];
+    }
+}
+
 }  // namespace icpb

@@ -7,6 +7,7 @@ Same names, argument meaning and return contracts as the reference module:
 * ``icp_iteration(pc1, pc2, previous_transform, rotation_only=False)
   -> (trans_mat, correspondences, error)``                                     (src/icp.py:55-69)
 * ``get_correspondences`` / ``get_closest_point``                              (src/icp.py:4-19)
+* ``get_transform`` / ``get_error``                                            (src/icp.py:22-52)
 
 plus the batched entry point ``icp_batch`` that replaces the reference's joblib fan-outs
 (scripts/main.py:240-247, src/loop_closure_detection.py:134-142,
@@ -26,6 +27,7 @@ from . import _lib
 from ._lib import IcpbError  # noqa: F401  (re-exported)
 
 __all__ = ["icp", "icp_iteration", "icp_batch", "get_correspondences", "get_closest_point",
+           "get_transform", "get_error",
            "ScanTable", "IcpEngine", "BatchResult", "engine"]
 
 
@@ -404,6 +406,29 @@ def get_closest_point(point, pc):
     """Reference ``get_closest_point`` (src/icp.py:4-7): index of the row of ``pc`` nearest to ``point``."""
     point = np.asarray(point, dtype=np.float64).reshape(1, -1)
     return get_correspondences(point, pc)[0]
+
+
+def _fit(pc1, pc2):
+    a, b = _cloud_xy(pc1, "pc1"), _cloud_xy(pc2, "pc2")
+    if len(a) != len(b):
+        raise ValueError("pc1 and pc2 must have the same number of rows (pc1[i] corresponds to pc2[i])")
+    e = engine()
+    T6 = np.empty(6)
+    err = ctypes.c_double()
+    _lib.check(e._L.icpb_fit_pairs_host(e._h, _ptr(a), _ptr(b), len(a), _ptr(T6), ctypes.byref(err)),
+               "icpb_fit_pairs_host")
+    return _to33(T6), np.float64(err.value)
+
+
+def get_transform(pc1, pc2):
+    """Reference ``get_transform`` (src/icp.py:22-46): the SE(2) matrix that best moves pc1[i] onto
+    pc2[i] (rows correspond)."""
+    return _fit(pc1, pc2)[0]
+
+
+def get_error(pc1, pc2):
+    """Reference ``get_error`` (src/icp.py:49-52): sum of squared differences of corresponding rows."""
+    return _fit(pc1, pc2)[1]
 
 
 def icp_batch(scans, pairs, init_transforms=None, epsilon=0.01, max_iters=100, stopping_thresh=0.0001,

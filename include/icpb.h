@@ -123,6 +123,12 @@ int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,
                        const icpb_params *p, double *h_T6, double *h_err, int32_t *h_passes,
                        double *h_hist, int32_t *h_corr);
 
+/* Rigid fit of n matched pairs a[i] -> b[i] ((n, 2) float64 host arrays) and their sum of squared
+ * differences: the reference's get_transform(pc1, pc2) (src/icp.py:22-46) and get_error(pc1, pc2)
+ * (src/icp.py:49-52), which assume pc1[i] corresponds to pc2[i]. */
+int icpb_fit_pairs_host(icpb_handle h, const double *h_a_xy, const double *h_b_xy, int64_t n,
+                        double *h_T6, double *h_err);
+
 /* Launch geometry and resource use of the alignment kernel for the current scan table
  * (reported by bench.py next to the roofline numbers). */
 typedef struct icpb_kernel_info {

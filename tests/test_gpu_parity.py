@@ -307,3 +307,23 @@ def test_pipelined_align_equals_upload_then_run(gicp):
     d = e.run(pairs, None, epsilon=0.05, max_iters=5)
     np.testing.assert_array_equal(c.T, d.T)
     e.close()
+
+
+def test_helper_functions(gicp, c_oracle):
+    """get_transform / get_error / get_correspondences / get_closest_point (src/icp.py:4-52)."""
+    from oracle import icp_oracle as po
+    rng = np.random.default_rng(21)
+    a = rng.uniform(-6, 6, size=(333, 2))
+    th = 0.3
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    b = a @ R.T + np.array([0.4, -0.7]) + rng.normal(0, 0.01, size=a.shape)
+    T = gicp.get_transform(hom(a), hom(b))
+    np.testing.assert_allclose(T, po.rigid_fit(hom(a), hom(b)), atol=1e-12)
+    e = gicp.get_error(hom(a), hom(b))
+    assert isinstance(e, np.float64)
+    np.testing.assert_allclose(e, np.sum((hom(a) - hom(b)) ** 2), rtol=1e-13)
+    corr = gicp.get_correspondences(hom(a), hom(b))
+    np.testing.assert_array_equal(corr, po.nearest_indices(hom(a), hom(b)))
+    assert gicp.get_closest_point(hom(a)[17], hom(b)) == corr[17]
+    with pytest.raises(ValueError):
+        gicp.get_transform(hom(a), hom(b[:10]))
