@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans", type=int, default=5000, help="scans in the chain (config: 5000)")
     ap.add_argument("--beams", type=int, default=1024, help="beams per scan (config: 1024)")
+    ap.add_argument("--workload", default="chain", choices=["chain", "proximity", "allpairs", "highres"])
+    ap.add_argument("--pairs", type=int, default=0, help="cap on the pair count of the non-chain workloads")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
@@ -58,16 +60,46 @@ def parse():
 
 
 def workload(args, rank, world):
+    """Synthetic scans + pair list + initial guesses of one rank.  `chain` is the headline
+    workload (BASELINE configs[1]); the others are the remaining BASELINE configs at a size that
+    fits a default run, for information (python bench.py --workload ...)."""
     from icp_slam_b200 import synth
     # each rank owns a different stretch of the trajectory and its own noise/odometry seed
     rng_seed = SEED + 1000 * rank
     rng = np.random.default_rng(rng_seed)
-    poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=rank / max(world, 1))
-    scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
-    odo = synth.odometry_from_truth(poses, rng)
-    idx = np.arange(1, args.scans)
-    pairs = np.stack((idx, idx - 1), axis=1).astype(np.int32)
-    init = np.stack([synth.pose_to_mat(odo[i] - odo[i - 1]) for i in idx])
+    phase = rank / max(world, 1)
+    if args.workload == "chain":            # configs[1]: scripts/main.py:239-247
+        poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=phase)
+        scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
+        odo = synth.odometry_from_truth(poses, rng)
+        idx = np.arange(1, args.scans)
+        pairs = np.stack((idx, idx - 1), axis=1).astype(np.int32)
+        init = np.stack([synth.pose_to_mat(odo[i] - odo[i - 1]) for i in idx])
+        args.label = f"odometry chain {args.scans} scans x {args.beams} beams per GPU (configs[1])"
+    elif args.workload == "proximity":      # configs[2]: all pairs within 1 m, >= 2 m along the path
+        poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=phase)
+        scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
+        pairs = synth.proximity_pairs(poses, max_pairs=args.pairs or 100000, seed=rng_seed)
+        init = np.broadcast_to(np.eye(3), (len(pairs), 3, 3)).copy()
+        args.label = f"proximity loop-closure candidates, {args.scans} scans x {args.beams} beams (configs[2])"
+    elif args.workload == "allpairs":       # configs[3]: exhaustive i<j, source j onto target i
+        poses = synth.loop_trajectory(args.scans, step=180.0 / args.scans, start_phase=phase)
+        scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
+        ij = synth.all_pairs_decode(np.arange(synth.all_pairs_count(args.scans)), args.scans)
+        pairs = np.stack((ij[:, 1], ij[:, 0]), axis=1).astype(np.int32)
+        if args.pairs and args.pairs < len(pairs):
+            pairs = pairs[np.sort(rng.choice(len(pairs), args.pairs, replace=False))]
+        init = np.broadcast_to(np.eye(3), (len(pairs), 3, 3)).copy()
+        args.label = f"all pairs i<j of {args.scans} scans x {args.beams} beams (configs[3])"
+    else:                                   # configs[4]: high-resolution scans, multi-start heading sweep
+        k_starts = 32
+        poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=phase)
+        scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
+        idx = np.repeat(np.arange(1, args.scans), k_starts)
+        pairs = np.stack((idx, idx - 1), axis=1).astype(np.int32)
+        th = np.tile(-np.pi + 2 * np.pi * np.arange(k_starts) / k_starts, args.scans - 1)
+        init = np.stack([synth.pose_to_mat((0.0, 0.0, t)) for t in th])
+        args.label = f"{k_starts}-start heading sweep, {args.scans} scans x {args.beams} beams (configs[4])"
     return scans, pairs, init
 
 
@@ -171,7 +203,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"odometry chain {args.scans} scans x {args.beams} beams (configs[1])",
+        "config": {"workload": args.label,
                    "pairs_per_step": n, "epsilon": 0.05, "max_iters": 100},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -372,8 +404,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 filter + f64 decide/accumulate",
             "data": "synthetic",
-            "config": {"workload": f"odometry chain {args.scans} scans x {args.beams} beams per GPU (configs[1]), "
-                                   f"{B} pairs per GPU per step",
+            "config": {"workload": f"{args.label}, {B} pairs per GPU per step",
                        "pairs_per_step": world * B, "epsilon": 0.05, "max_iters": 100,
                        "mean_passes": float(passes.mean()), "l2": "flushed between timed steps (768 MB fill)",
                        "collective": "all_gather of (B,8) f64 constraint records" if world > 1 else "none",
