@@ -8,6 +8,7 @@ maps stay the reference's own code (out of scope).
 * ``odometry_chain``            -- scripts/main.py:239-256 (ICP fan-out + chain composition)
 * ``proximity_candidates``      -- src/loop_closure_detection.py:12-25 (candidate generation)
 * ``proximity_loop_closures``   -- src/loop_closure_detection.py:26-39 (ICP + greedy acceptance)
+* ``image_match_loop_closures`` -- src/loop_closure_detection.py:134-159 (ICP over image matches)
 * ``rotation_only_headings``    -- src/pose_graph_optimization.py:59-74
 """
 from __future__ import annotations
@@ -90,6 +91,23 @@ def proximity_loop_closures(poses, lidar_points, min_dist_along_path=2, max_dist
             out.append((i, j, T))
             used.add(i)
             used.add(j)
+    return out, res
+
+
+def image_match_loop_closures(good_matches, lidar_points, image_rate=1, icp_err_thresh=30, max_iters=100,
+                              epsilon=0.05, device=None):
+    """ICP block of the reference's ``detect_images_direct_similarity``
+    (src/loop_closure_detection.py:134-159): for every image match (i, j) align scan
+    ``i*image_rate`` (source) onto scan ``j*image_rate`` (target) from the identity -- note the
+    argument order is the opposite of ``detect_proximity``'s, a reference quirk kept as is -- and
+    keep the pairs with error < icp_err_thresh.  Returns [(i*rate, j*rate, T)] in match order, and
+    the BatchResult.  The ORB/matcher front end that produces ``good_matches`` is out of scope."""
+    gm = np.asarray(good_matches, dtype=np.int64).reshape(-1, 2)
+    if len(gm) == 0:
+        return [], None
+    pairs = (gm * image_rate).astype(np.int32)               # (source = i*rate, target = j*rate)
+    res = _icp.icp_batch(lidar_points, pairs, None, epsilon=epsilon, max_iters=max_iters, device=device)
+    out = [(int(i), int(j), T) for (i, j), T, e in zip(pairs, res.T, res.error) if e < icp_err_thresh]
     return out, res
 
 

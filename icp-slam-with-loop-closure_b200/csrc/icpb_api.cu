@@ -57,14 +57,16 @@ struct DevBuf {
 
 struct LaunchCfg {
     int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ntile_cap, ctas_per_sm;
+    int cluster;   // CTAs per problem (1 = ordinary launch)
 };
 
 typedef void (*kernel_fn)(const icpb::KernelArgs);
 kernel_fn pick_kernel(const icpb_params *p)
 {
-    return (p && (p->flags & ICPB_FLAG_EXHAUSTIVE)) ? icpb::icp_align_kernel<kPointsPerThread, false>
-                                                    : icpb::icp_align_kernel<kPointsPerThread, true>;
+    return (p && (p->flags & ICPB_FLAG_EXHAUSTIVE)) ? icpb::icp_align_kernel<kPointsPerThread, false, false>
+                                                    : icpb::icp_align_kernel<kPointsPerThread, true, false>;
 }
+kernel_fn cluster_kernel() { return icpb::icp_align_kernel<kPointsPerThread, true, true>; }
 
 }  // namespace
 
@@ -117,10 +119,26 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     if (threads < 32) threads = 32;
     c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
     c->nchunk_cap = (int)nchunk; c->ntile_cap = (int)ntile;
+    // Latency mode: with fewer problems than SMs and more tiles than one CTA has warps, spread each
+    // problem over a thread-block cluster (a power of two, at most 8 CTAs) so every tile gets a warp.
+    c->cluster = 1;
+    if (fn == pick_kernel(nullptr) && B * 2 <= h->sm_count && ntile > 8) {
+        int cl = 2;
+        while (cl < 8 && (int64_t)cl * 8 < ntile) cl *= 2;
+        while (cl > 1 && B * cl > h->sm_count) cl /= 2;
+        c->cluster = cl;
+    }
+    if (const char *t = getenv("ICPB_CLUSTER")) {         // tuning / tests: force a cluster size (0 = never)
+        const int v = atoi(t);
+        if (v == 0 || v == 1) c->cluster = 1;
+        else if ((v == 2 || v == 4 || v == 8) && fn == pick_kernel(nullptr)) c->cluster = v;
+    }
     if ((int)smem > h->max_smem_set) {
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true>,
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, false>,
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, false, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->max_smem_set = (int)smem;
     }
@@ -164,7 +182,20 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
     if (grid > B) grid = B;
-    fn<<<(unsigned)grid, cfg.threads, cfg.smem, stream>>>(a);
+    if (cfg.cluster > 1) {
+        cudaLaunchConfig_t lc = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cfg.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        int64_t clusters = grid / cfg.cluster;              // resident CTAs -> clusters
+        if (clusters < 1) clusters = 1;
+        if (clusters > B) clusters = B;
+        lc.gridDim = dim3((unsigned)(clusters * cfg.cluster)); lc.blockDim = dim3((unsigned)cfg.threads);
+        lc.dynamicSmemBytes = (size_t)cfg.smem; lc.stream = stream; lc.attrs = attr; lc.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&lc, cluster_kernel(), a));
+    } else {
+        fn<<<(unsigned)grid, cfg.threads, cfg.smem, stream>>>(a);
+    }
     CU(cudaGetLastError());
     h->launches++;
     return 0;

@@ -20,6 +20,7 @@
 //     candidate of the exact decision, so the result is that of the exhaustive search.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include "icpb.h"
 
@@ -127,15 +128,12 @@ __device__ __forceinline__ float filter_tol(float m1, float px, float py, float 
 }
 
 // Rare path of the decision step: all targets j in [lo, hi) whose filter distance is <= thr are
-// evaluated exactly; returns the lexicographic (distance, index) minimum (j ascends, so strict <
-// keeps the first index = np.argmin's rule).  Not inlined: it runs for a fraction of a percent
-// of the points and would otherwise be replicated per register-tiled point.
-__device__ __noinline__ int exact_decide(int lo, int hi, int fallback, float thr, float px, float py,
-                                         double Px, double Py, const float *tqx, const float *tqy,
-                                         const double2 *dst)
+// evaluated exactly; keeps the lexicographic (distance, index) minimum (j ascends, so strict <
+// keeps the first index = np.argmin's rule).
+__device__ __forceinline__ void exact_range(int lo, int hi, float thr, float px, float py, double Px, double Py,
+                                            const float *tqx, const float *tqy, const double2 *dst,
+                                            double &best, int &idx)
 {
-    double best = __longlong_as_double(0x7ff0000000000000LL);
-    int idx = fallback;
     for (int j = lo; j < hi; ++j) {
         const float d = dist32(px, py, tqx[j], tqy[j]);
         if (d <= thr) {
@@ -143,6 +141,39 @@ __device__ __noinline__ int exact_decide(int lo, int hi, int fallback, float thr
             const double D = dist64(Px, Py, q.x, q.y);
             if (D < best) { best = D; idx = j; }
         }
+    }
+}
+
+// Not inlined: these run for a fraction of a percent of the points and would otherwise be
+// replicated per register-tiled point.
+// (a) several candidates inside the best chunk: bit k of `cand` marks target j0 + k
+__device__ __noinline__ int exact_decide_chunk(int j0, unsigned cand, double Px, double Py, const double2 *dst)
+{
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int idx = j0;
+    while (cand) {                                   // ascending k: strict < keeps the first index
+        const int j = j0 + __ffs(cand) - 1;
+        cand &= cand - 1;
+        const double2 q = dst[j];
+        const double D = dist64(Px, Py, q.x, q.y);
+        if (D < best) { best = D; idx = j; }
+    }
+    return idx;
+}
+// (b) another chunk is within the bound: every chunk whose circle reaches within sqrt(thr) of the
+// point may hold a candidate (chunks ascend, so the first-index rule still holds across chunks)
+__device__ __noinline__ int exact_decide_all(int nchunks, int n2, int fallback, float thr, float px, float py,
+                                             double Px, double Py, const float *tqx, const float *tqy,
+                                             const float4 *cb, const double2 *dst)
+{
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int idx = fallback;
+    const float s = sqrt_fast(thr) * 1.0001f + 1e-30f;
+    for (int c = 0; c < nchunks; ++c) {
+        const float4 b = cb[c];
+        const float lim = (s + b.z) * 1.0001f;
+        if (dist32(px, py, b.x, b.y) <= lim * lim)
+            exact_range(c * kChunk, min(c * kChunk + kChunk, n2), thr, px, py, Px, Py, tqx, tqy, dst, best, idx);
     }
     return idx;
 }
@@ -231,7 +262,13 @@ __device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
 // A tile = 32*R consecutive source points = one warp's register tile.  Warps pull tiles from a
 // shared counter (tiles differ in how many chunks survive pruning); partial sums are stored per
 // tile and folded in tile order, so the result does not depend on which warp ran which tile.
-template <int R, bool PRUNE>
+//
+// CLUSTER = true (latency mode, few problems): one thread-block *cluster* of up to 8 CTAs per scan
+// pair.  Every CTA stages the target itself; the source tiles are dealt round-robin to the CTAs
+// (tile t belongs to CTA t mod cluster size); the per-tile partial sums stay in their owner's
+// shared memory and every CTA folds them over distributed shared memory after the pass's
+// cluster barrier -- in the same tile order as the single-CTA kernel, so the two give the same bits.
+template <int R, bool PRUNE, bool CLUSTER>
 #ifndef ICPB_MIN_CTAS
 #define ICPB_MIN_CTAS 3
 #endif
@@ -254,15 +291,32 @@ icp_align_kernel(const KernelArgs a)
     const float kInf = __int_as_float(0x7f800000);
     double *Tmine = Tw + warp * 6;
     unsigned int executed = 0;
+    namespace cg = cooperative_groups;
+    int crank = 0, csize = 1;
+    if (CLUSTER) {
+        cg::cluster_group cluster = cg::this_cluster();
+        crank = (int)cluster.block_rank();
+        csize = (int)cluster.num_blocks();
+    }
+    // block-wide barrier, cluster-wide in latency mode
+    auto sync_all = [&]() {
+        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+    };
 
     for (;;) {
         // ---------------- pop a problem ----------------
         if (tid == 0) {
-            s_pid = (long long)atomicAdd(a.queue, 1ULL);
+            if (!CLUSTER) {
+                s_pid = (long long)atomicAdd(a.queue, 1ULL);
+            } else if (crank == 0) {                       // one pop per cluster, broadcast over DSMEM
+                const long long v = (long long)atomicAdd(a.queue, 1ULL);
+                cg::cluster_group cluster = cg::this_cluster();
+                for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(&s_pid, r) = v;
+            }
             s_qmax_bits = 0u;
             s_tile_ctr[0] = 0; s_tile_ctr[1] = 0;
         }
-        __syncthreads();
+        sync_all();
         const int64_t pid = s_pid;
         if (pid >= a.B) break;
 
@@ -335,6 +389,7 @@ icp_align_kernel(const KernelArgs a)
                 int tile = 0;
                 if (lane == 0) tile = atomicAdd(&s_tile_ctr[passes & 1], 1);
                 tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (CLUSTER) tile = crank + tile * csize;        // this CTA owns tiles crank, crank + csize, ...
                 if (tile >= ntiles) break;
                 const int i0 = (tile * 32 + lane) * R;
                 // ---- transform, upper bounds, tile bounding circle ----
@@ -496,23 +551,23 @@ icp_align_kernel(const KernelArgs a)
 #pragma unroll
                                 for (int v = 0; v < 4; ++v) dist32x4(PX, PY, bx[v], by[v], d + 4 * v);
                             }
-                            int cntpos = 0;                      // candidates * 256 + sum of their positions
-                            // one FSETP + one predicated IADD per target
-#define ICPB_CAND(K) asm("{ .reg .pred q; setp.le.f32 q, %1, %2; @q add.s32 %0, %0, %3; }" \
-                         : "+r"(cntpos) : "f"(d[K]), "f"(thr), "n"(256 + K))
+                            unsigned cand = 0;                   // bit k: target j0 + k is a candidate
+                            // one FSETP + one predicated LOP per target
+#define ICPB_CAND(K) asm("{ .reg .pred q; setp.le.f32 q, %1, %2; @q or.b32 %0, %0, %3; }" \
+                         : "+r"(cand) : "f"(d[K]), "f"(thr), "n"(1 << K))
                             ICPB_CAND(0);  ICPB_CAND(1);  ICPB_CAND(2);  ICPB_CAND(3);
                             ICPB_CAND(4);  ICPB_CAND(5);  ICPB_CAND(6);  ICPB_CAND(7);
                             ICPB_CAND(8);  ICPB_CAND(9);  ICPB_CAND(10); ICPB_CAND(11);
                             ICPB_CAND(12); ICPB_CAND(13); ICPB_CAND(14); ICPB_CAND(15);
 #undef ICPB_CAND
                             static_assert(kChunk == 16, "candidate count is written out for 16 targets");
-                            const int cnt = cntpos >> 8;
-                            int idx = j0 + (cntpos & 255);       // unique candidate: no fp64 needed
+                            int idx = j0 + __ffs(cand) - 1;      // unique candidate: no fp64 needed
                             if (m2[r] <= thr)                    // another chunk is within the bound
-                                idx = exact_decide(0, n2, j0, thr, px[r], py[r], Px, Py, tqx, tqy, dst);
-                            else if (cnt != 1)
-                                idx = exact_decide(j0, min(j0 + kChunk, n2), j0, thr, px[r], py[r], Px, Py,
-                                                   tqx, tqy, dst);
+                                idx = exact_decide_all(nchunks, n2, j0, thr, px[r], py[r], Px, Py, tqx, tqy, cb, dst);
+                            else if (cand & (cand - 1))          // more than one candidate in the chunk
+                                idx = exact_decide_chunk(j0, cand, Px, Py, dst);
+                            else if (cand == 0)                  // (non-finite input: keep a valid index)
+                                idx = j0;
                             corr_s[i] = idx;
                             const double2 q = dst[idx];
                             const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
@@ -535,7 +590,7 @@ icp_align_kernel(const KernelArgs a)
             }
 
             // =========== fit (src/icp.py:22-52): deterministic reduction, one barrier per pass ===========
-            __syncthreads();
+            sync_all();
             if (tid == 0) s_tile_ctr[passes & 1] = 0;          // next used two passes from now
             // every warp folds the tile partials in the same fixed order and updates its own copy of T:
             // lane k + 9*part (part 0..2) adds column k over tiles = part (mod 3), in tile order
@@ -544,7 +599,13 @@ icp_align_kernel(const KernelArgs a)
                 double col = 0.0;
                 if (lane < 3 * kNumSums) {
                     const int k = lane % kNumSums;
-                    for (int t = lane / kNumSums; t < ntiles; t += 3) col += redp[t * kNumSums + k];
+                    if (!CLUSTER) {
+                        for (int t = lane / kNumSums; t < ntiles; t += 3) col += redp[t * kNumSums + k];
+                    } else {                                     // tile t lives in CTA t mod csize
+                        cg::cluster_group cluster = cg::this_cluster();
+                        for (int t = lane / kNumSums; t < ntiles; t += 3)
+                            col += cluster.map_shared_rank(redp, t % csize)[t * kNumSums + k];
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < kNumSums; ++k)
@@ -591,7 +652,7 @@ icp_align_kernel(const KernelArgs a)
                 if (lane == 0) {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) Tmine[k] = N[k];
-                    if (warp == 0 && a.hist && passes < a.p.hist_cap) {
+                    if (warp == 0 && crank == 0 && a.hist && passes < a.p.hist_cap) {
                         double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
 #pragma unroll
                         for (int k = 0; k < 6; ++k) hrow[k] = N[k];
@@ -608,7 +669,7 @@ icp_align_kernel(const KernelArgs a)
             last_err = err; have_last = true;
             ++iteration;
         }
-        if (tid == 0) {
+        if (tid == 0 && crank == 0) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = Tmine[k];
             a.err_out[pid] = err;
@@ -617,9 +678,10 @@ icp_align_kernel(const KernelArgs a)
         if (a.corr) {
             int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;
             const int lim = min(n1, a.p.corr_stride);
-            for (int i = tid; i < lim; i += NT) crow[i] = corr_s[i];
+            for (int i = tid; i < lim; i += NT)
+                if (!CLUSTER || (i / (32 * R)) % csize == crank) crow[i] = corr_s[i];   // own tiles only
         }
-        __syncthreads();        // smem is reused by the next problem
+        sync_all();             // smem is reused by the next problem (remote reads of red included)
     }
     if (a.executed) {
         // chunks processed by this warp x 16 targets x 32*R source-point slots

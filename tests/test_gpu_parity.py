@@ -327,3 +327,37 @@ def test_helper_functions(gicp, c_oracle):
     assert gicp.get_closest_point(hom(a)[17], hom(b)) == corr[17]
     with pytest.raises(ValueError):
         gicp.get_transform(hom(a), hom(b[:10]))
+
+
+@pytest.mark.parametrize("n_beams,cluster", [(1024, 2), (4096, 8), (4096, 4), (700, 2)])
+def test_cluster_latency_mode_bit_identical(gicp, n_beams, cluster):
+    """Latency mode: one thread-block cluster per pair, tiles dealt to the CTAs, partial sums folded
+    over distributed shared memory in the same order -> the same bits as the single-CTA kernel."""
+    import os
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(n_beams + cluster)
+    poses = synth.loop_trajectory(6, step=0.08)
+    scans = synth.scans_from_poses(poses, n_beams, rng, drop_frac=0.03)
+    pairs = np.array([(1, 0), (2, 1), (5, 2), (3, 3)], dtype=np.int32)
+    e = gicp.IcpEngine()
+    e.set_scans(scans)
+    old = os.environ.get("ICPB_CLUSTER")
+    try:
+        os.environ["ICPB_CLUSTER"] = "0"
+        a = e.run(pairs, None, epsilon=0.05, max_iters=100, return_history=True, return_correspondences=True)
+        os.environ["ICPB_CLUSTER"] = str(cluster)
+        b = e.run(pairs, None, epsilon=0.05, max_iters=100, return_history=True, return_correspondences=True)
+        os.environ.pop("ICPB_CLUSTER")
+        c = e.run(pairs[:1], None, epsilon=0.05, max_iters=100)          # automatic choice for one pair
+    finally:
+        if old is None:
+            os.environ.pop("ICPB_CLUSTER", None)
+        else:
+            os.environ["ICPB_CLUSTER"] = old
+    np.testing.assert_array_equal(a.T, b.T)
+    np.testing.assert_array_equal(a.error, b.error)
+    np.testing.assert_array_equal(a.iters, b.iters)
+    np.testing.assert_array_equal(a.history, b.history)
+    np.testing.assert_array_equal(a.correspondences, b.correspondences)
+    np.testing.assert_array_equal(a.T[:1], c.T)
+    e.close()

@@ -41,3 +41,21 @@ def test_pipeline_matches_reference_golden():
     start = slam_oracle.tangent_headings(z["optimised"])
     re, _ = callers.rotation_only_headings(start, scans, max_iters=100, epsilon=0.05)
     np.testing.assert_allclose(re, z["reoriented"], atol=1e-8)
+
+
+def test_image_match_call_site():
+    """src/loop_closure_detection.py:134-159: source = scan i*rate, target = scan j*rate, identity
+    initial guess, accepted when error < icp_err_thresh."""
+    from icp_slam_b200 import callers
+    from oracle import c_oracle
+    z, scans = load()
+    good = [(3, 1), (10, 12), (20, 49), (7, 7)]
+    rate = 3
+    out, res = callers.image_match_loop_closures(good, scans, image_rate=rate, icp_err_thresh=30)
+    xy, off = c_oracle.pack(scans)
+    pairs = np.array([(i * rate, j * rate) for i, j in good], dtype=np.int32)
+    T, err, passes = c_oracle.icp_batch(xy, off, pairs, None, epsilon=0.05, max_iters=100)
+    np.testing.assert_array_equal(res.iters, passes)
+    np.testing.assert_allclose(res.T, T, atol=1e-9)
+    keep = [(int(p[0]), int(p[1])) for p, e in zip(pairs, err) if e < 30]
+    assert [(a, b) for a, b, _ in out] == keep and (21, 21) in keep
