@@ -18,7 +18,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
 EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destroy",
            "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
-           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host"]
+           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host",
+           "icpb_proximity_closest", "icpb_proximity_pairs"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -45,6 +46,7 @@ class IcpbError(RuntimeError):
 def sources():
     c = os.path.join(_HERE, "csrc")
     return [os.path.join(c, "icpb_api.cu")], [os.path.join(c, "icpb_kernels.cuh"),
+                                              os.path.join(c, "icpb_candidates.cuh"),
                                               os.path.join(_ROOT, "include", "icpb.h")]
 
 
@@ -84,6 +86,9 @@ def lib() -> ctypes.CDLL:
     L.icpb_run_device.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p, vp]
     L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_align_host.argtypes = [vp, dp, vp, i64, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p]
+    L.icpb_proximity_closest.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i32p, dp]
+    L.icpb_proximity_pairs.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i64, i32p,
+                                       ctypes.POINTER(ctypes.c_int64)]
     L.icpb_fit_pairs_host.argtypes = [vp, dp, dp, i64, dp, dp]
     L.icpb_icp_pair_host.argtypes = [vp, dp, i64, dp, i64, dp, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_get_kernel_info.argtypes = [vp, i64, ctypes.POINTER(IcpbKernelInfo)]

@@ -6,7 +6,8 @@ the caller's remaining host code consumes.  The pose graph container, the SGD re
 maps stay the reference's own code (out of scope).
 
 * ``odometry_chain``            -- scripts/main.py:239-256 (ICP fan-out + chain composition)
-* ``proximity_candidates``      -- src/loop_closure_detection.py:12-25 (candidate generation)
+* ``proximity_candidates``      -- src/loop_closure_detection.py:12-25 (candidate generation, GPU)
+* ``proximity_pairs``           -- the same rule keeping every pair within the radius (config 3)
 * ``proximity_loop_closures``   -- src/loop_closure_detection.py:26-39 (ICP + greedy acceptance)
 * ``image_match_loop_closures`` -- src/loop_closure_detection.py:134-159 (ICP over image matches)
 * ``rotation_only_headings``    -- src/pose_graph_optimization.py:59-74
@@ -44,27 +45,51 @@ def odometry_chain(lidar_points, odometry, max_iters=100, epsilon=0.05, device=N
     return poses, res
 
 
-def proximity_candidates(poses, min_dist_along_path=2, max_dist=1):
+def _travelled(xy: np.ndarray) -> np.ndarray:
+    """The reference's ``dist_traveled`` (src/loop_closure_detection.py:13-14): cumulative sum of the
+    consecutive pose distances, first entry 0.  O(S) on the host, in numpy's summation order."""
+    step = np.sqrt((xy[1:, 0] - xy[:-1, 0]) ** 2 + (xy[1:, 1] - xy[:-1, 1]) ** 2)
+    return np.concatenate(([0.0], np.cumsum(step)))
+
+
+def proximity_candidates(poses, min_dist_along_path=2, max_dist=1, device=None):
     """At most one candidate per pose i: the Euclidean-closest pose j among those at least
     ``min_dist_along_path`` further along the path, kept if within ``max_dist``
-    (src/loop_closure_detection.py:12-25).  Returned in the reference's processing order
-    (its ``matches.reverse()``), as an (M, 2) array of (i, j)."""
-    xy = np.asarray(poses, dtype=np.float64)[:, :2]
+    (src/loop_closure_detection.py:12-25).  The S x S cdist matrix of the reference is never
+    built: one warp per pose scans its row on the GPU (icpb_proximity_closest).  Returned in the
+    reference's processing order (its ``matches.reverse()``), as an (M, 2) array of (i, j)."""
+    import ctypes
+    xy = np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :2])
     n = len(xy)
-    step = np.sqrt((xy[1:, 0] - xy[:-1, 0]) ** 2 + (xy[1:, 1] - xy[:-1, 1]) ** 2)
-    travelled = np.concatenate(([0.0], np.cumsum(step)))
-    first = np.searchsorted(travelled, travelled + min_dist_along_path, side="right")
-    out = []
-    for i in range(n):
-        j0 = first[i]
-        if j0 >= n:
-            break                                            # the reference stops at the first such i
-        d = np.sqrt((xy[j0:, 0] - xy[i, 0]) ** 2 + (xy[j0:, 1] - xy[i, 1]) ** 2)
-        j = j0 + int(np.argmin(d))
-        if d[j - j0] <= max_dist:
-            out.append((i, j))
-    out.reverse()
-    return np.asarray(out, dtype=np.int64).reshape(-1, 2)
+    trav = _travelled(xy)
+    closest = np.empty(n, dtype=np.int32)
+    dist = np.empty(n)
+    e = _icp.engine(device)
+    _icp._lib.check(e._L.icpb_proximity_closest(e._h, _icp._ptr(xy), _icp._ptr(trav), n,
+                                                ctypes.c_double(min_dist_along_path), ctypes.c_double(max_dist),
+                                                _icp._ptr(closest), _icp._ptr(dist)), "icpb_proximity_closest")
+    i = np.nonzero(closest >= 0)[0]
+    out = np.stack((i, closest[i].astype(np.int64)), axis=1)[::-1]
+    return np.ascontiguousarray(out, dtype=np.int64).reshape(-1, 2)
+
+
+def proximity_pairs(poses, min_dist_along_path=2, max_dist=1, device=None) -> np.ndarray:
+    """Every pair within the radius (BASELINE config 3's generalisation of detect_proximity): all
+    (i, j) with j at least ``min_dist_along_path`` further along the path than i and within
+    ``max_dist``, as (source = j, target = i) int32 rows ordered by i then j."""
+    import ctypes
+    xy = np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :2])
+    n = len(xy)
+    trav = _travelled(xy)
+    e = _icp.engine(device)
+    total = ctypes.c_int64()
+    args = (e._h, _icp._ptr(xy), _icp._ptr(trav), n, ctypes.c_double(min_dist_along_path), ctypes.c_double(max_dist))
+    _icp._lib.check(e._L.icpb_proximity_pairs(*args, 0, None, ctypes.byref(total)), "icpb_proximity_pairs")
+    pairs = np.empty((total.value, 2), dtype=np.int32)
+    if total.value:
+        _icp._lib.check(e._L.icpb_proximity_pairs(*args, total.value, _icp._ptr(pairs), ctypes.byref(total)),
+                        "icpb_proximity_pairs")
+    return pairs
 
 
 def proximity_loop_closures(poses, lidar_points, min_dist_along_path=2, max_dist=1, err_thresh=110,
@@ -76,7 +101,7 @@ def proximity_loop_closures(poses, lidar_points, min_dist_along_path=2, max_dist
     loop -- skip a candidate if either endpoint was already used by an *accepted* one, accept if
     error < err_thresh -- is replayed on the results (:27-39).  Returns a list of
     (i, j, T 3x3) ready for ``pose_graph.add_constraint(i, j, T)``, and the BatchResult."""
-    cand = proximity_candidates(poses, min_dist_along_path, max_dist)
+    cand = proximity_candidates(poses, min_dist_along_path, max_dist, device)
     if len(cand) == 0:
         return [], None
     pairs = np.stack((cand[:, 1], cand[:, 0]), axis=1).astype(np.int32)

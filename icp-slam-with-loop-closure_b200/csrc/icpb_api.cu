@@ -11,6 +11,7 @@
 
 #include "icpb.h"
 #include "icpb_kernels.cuh"
+#include "icpb_candidates.cuh"
 
 namespace {
 
@@ -563,6 +564,77 @@ int icpb_fit_pairs_host(icpb_handle h, const double *h_a_xy, const double *h_b_x
     CU(cudaStreamSynchronize(h->stream));
     memcpy(h_T6, out, 6 * sizeof(double));
     *h_err = out[6];
+    return 0;
+}
+
+static int upload_poses(icpb_handle h, const double *h_xy, const double *h_travelled, int64_t n,
+                        double **d_xy, double **d_trav)
+{
+    int rc;
+    if ((rc = h->s_pair_xy.reserve(sizeof(double) * 3 * (size_t)n))) return rc;
+    *d_xy = (double *)h->s_pair_xy.p;
+    *d_trav = *d_xy + 2 * n;
+    CU(cudaMemcpyAsync(*d_xy, h_xy, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(*d_trav, h_travelled, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int icpb_proximity_closest(icpb_handle h, const double *h_xy, const double *h_travelled, int64_t n,
+                           double min_dist_along_path, double max_dist, int32_t *h_closest, double *h_dist)
+{
+    if (!h || !h_xy || !h_travelled || n <= 0 || n > 0x3fffffff || !h_closest || !h_dist)
+        return fail(ICPB_EINVAL, "icpb_proximity_closest: bad argument%s");
+    CU(cudaSetDevice(h->device));
+    double *d_xy, *d_trav;
+    int rc = upload_poses(h, h_xy, h_travelled, n, &d_xy, &d_trav);
+    if (rc) return rc;
+    if ((rc = h->s_passes.reserve(sizeof(int32_t) * (size_t)n))) return rc;
+    if ((rc = h->s_err.reserve(sizeof(double) * (size_t)n))) return rc;
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    icpb::proximity_closest_kernel<<<grid, 256, 0, h->stream>>>((const double2 *)d_xy, d_trav, (int)n,
+                                                                min_dist_along_path, max_dist,
+                                                                (int32_t *)h->s_passes.p, (double *)h->s_err.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_closest, h->s_passes.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h_dist, h->s_err.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int icpb_proximity_pairs(icpb_handle h, const double *h_xy, const double *h_travelled, int64_t n,
+                         double min_dist_along_path, double max_dist, int64_t capacity,
+                         int32_t *h_pairs, int64_t *n_pairs)
+{
+    if (!h || !h_xy || !h_travelled || n <= 0 || n > 0x3fffffff || !n_pairs || capacity < 0 ||
+        (capacity > 0 && !h_pairs))
+        return fail(ICPB_EINVAL, "icpb_proximity_pairs: bad argument%s");
+    CU(cudaSetDevice(h->device));
+    double *d_xy, *d_trav;
+    int rc = upload_poses(h, h_xy, h_travelled, n, &d_xy, &d_trav);
+    if (rc) return rc;
+    if ((rc = h->s_T.reserve(sizeof(int64_t) * 2 * (size_t)n))) return rc;
+    int64_t *d_count = (int64_t *)h->s_T.p, *d_off = d_count + n;
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    icpb::proximity_pairs_kernel<false><<<grid, 256, 0, h->stream>>>((const double2 *)d_xy, d_trav, (int)n,
+                                                                     min_dist_along_path, max_dist,
+                                                                     d_count, nullptr, nullptr);
+    CU(cudaGetLastError());
+    std::vector<int64_t> cnt((size_t)n), off((size_t)n);
+    CU(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; ++i) { off[i] = total; total += cnt[i]; }      // S values: a host scan is enough
+    *n_pairs = total;
+    if (capacity == 0 || total == 0) return 0;                                // size query
+    if (total > capacity) return fail(ICPB_EINVAL, "icpb_proximity_pairs: capacity too small%s");
+    if ((rc = h->s_pairs.reserve(sizeof(int32_t) * 2 * (size_t)total))) return rc;
+    CU(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    icpb::proximity_pairs_kernel<true><<<grid, 256, 0, h->stream>>>((const double2 *)d_xy, d_trav, (int)n,
+                                                                    min_dist_along_path, max_dist,
+                                                                    nullptr, d_off, (int32_t *)h->s_pairs.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_pairs, h->s_pairs.p, sizeof(int32_t) * 2 * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

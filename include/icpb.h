@@ -129,6 +129,25 @@ int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,
 int icpb_fit_pairs_host(icpb_handle h, const double *h_a_xy, const double *h_b_xy, int64_t n,
                         double *h_T6, double *h_err);
 
+/*
+ * Loop-closure candidate generation: the front half of detect_proximity
+ * (src/loop_closure_detection.py:12-25) without the S x S cdist matrix.  h_xy is the (n, 2)
+ * position part of pose_graph.poses, h_travelled the reference's dist_traveled array (:13-14:
+ * cumulative sum of consecutive distances, first entry 0).  For every pose i, start =
+ * searchsorted(travelled, travelled[i] + min_dist_along_path, "right") (:18); h_closest[i] is
+ * start + argmin(dist[i, start:]) (:21) if that distance is <= max_dist (:22), else -1 (also
+ * when start is past the end, where the reference stops, :19-20).
+ */
+int icpb_proximity_closest(icpb_handle h, const double *h_xy, const double *h_travelled, int64_t n,
+                           double min_dist_along_path, double max_dist, int32_t *h_closest, double *h_dist);
+
+/* The generalisation BASELINE config 3 names: EVERY pair (i, j), j >= start(i), within max_dist,
+ * as (source = j, target = i) rows (the argument order of :31-34), ordered by i then j.  Call with
+ * capacity 0 to get the count in *n_pairs, then again with a buffer of that many rows. */
+int icpb_proximity_pairs(icpb_handle h, const double *h_xy, const double *h_travelled, int64_t n,
+                         double min_dist_along_path, double max_dist, int64_t capacity,
+                         int32_t *h_pairs, int64_t *n_pairs);
+
 /* Launch geometry and resource use of the alignment kernel for the current scan table
  * (reported by bench.py next to the roofline numbers). */
 typedef struct icpb_kernel_info {

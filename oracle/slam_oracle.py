@@ -88,3 +88,23 @@ def tangent_headings(poses):
             v = v / nv
             poses[i][2] = np.arctan2(v[1], v[0])
     return poses
+
+
+def proximity_candidates_ref(poses, min_dist_along_path=2, max_dist=1):
+    """src/loop_closure_detection.py:12-25 restated with numpy rows instead of the cdist matrix;
+    returns (i, j) rows in the reference's processing order (after its matches.reverse())."""
+    xy = np.asarray(poses, dtype=np.float64)[:, :2]
+    n = len(xy)
+    step = np.sqrt((xy[1:, 0] - xy[:-1, 0]) ** 2 + (xy[1:, 1] - xy[:-1, 1]) ** 2)
+    travelled = np.concatenate(([0.0], np.cumsum(step)))
+    out = []
+    for i in range(n):
+        j0 = int(np.searchsorted(travelled, travelled[i] + min_dist_along_path, side="right"))
+        if j0 >= n:
+            break
+        d = np.sqrt((xy[j0:, 0] - xy[i, 0]) ** 2 + (xy[j0:, 1] - xy[i, 1]) ** 2)
+        j = j0 + int(np.argmin(d))
+        if d[j - j0] <= max_dist:
+            out.append((i, j))
+    out.reverse()
+    return np.asarray(out, dtype=np.int64).reshape(-1, 2)

@@ -59,3 +59,22 @@ def test_image_match_call_site():
     np.testing.assert_allclose(res.T, T, atol=1e-9)
     keep = [(int(p[0]), int(p[1])) for p, e in zip(pairs, err) if e < 30]
     assert [(a, b) for a, b, _ in out] == keep and (21, 21) in keep
+
+
+def test_candidate_generation_on_gpu():
+    """icpb_proximity_closest / icpb_proximity_pairs against the numpy restatement of
+    src/loop_closure_detection.py:12-25 and against synth.proximity_pairs, on a 5,000-pose loop."""
+    from icp_slam_b200 import callers, synth
+    from oracle import slam_oracle
+    z, _ = load()
+    np.testing.assert_array_equal(callers.proximity_candidates(z["corrected"]),
+                                  slam_oracle.proximity_candidates_ref(z["corrected"]))
+    poses = synth.loop_trajectory(5000, step=0.04)
+    for kw in (dict(), dict(min_dist_along_path=5.0, max_dist=0.4), dict(min_dist_along_path=0.0, max_dist=0.1),
+               dict(min_dist_along_path=1e9)):
+        np.testing.assert_array_equal(callers.proximity_candidates(poses, **kw),
+                                      slam_oracle.proximity_candidates_ref(poses, **kw))
+    got = callers.proximity_pairs(poses)
+    want = synth.proximity_pairs(poses)
+    np.testing.assert_array_equal(got, want)
+    assert len(got) > 100000

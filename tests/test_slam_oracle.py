@@ -16,9 +16,8 @@ def load():
 
 
 def test_candidates_and_greedy_replay_match_detect_proximity():
-    from icp_slam_b200 import callers
     z, scans = load()
-    cand = callers.proximity_candidates(z["corrected"])
+    cand = slam_oracle.proximity_candidates_ref(z["corrected"])
     assert len(cand) > len(z["loop_ij"])
     xy, off = c_oracle.pack(scans)
     pairs = np.stack((cand[:, 1], cand[:, 0]), axis=1).astype(np.int32)
