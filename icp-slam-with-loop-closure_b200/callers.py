@@ -38,11 +38,20 @@ def odometry_chain(lidar_points, odometry, max_iters=100, epsilon=0.05, device=N
     pairs = chain_pairs(n)
     init = np.stack([pose_to_mat(odometry[i] - odometry[i - 1]) for i in range(1, n)])
     res = _icp.icp_batch(lidar_points, pairs, init, epsilon=epsilon, max_iters=max_iters, device=device)
-    poses = np.zeros((n, 3))
-    poses[0] = odometry[0]
-    for i in range(1, n):                                    # serial SE(2) prefix product (:249-256)
-        poses[i] = mat_to_pose(pose_to_mat(poses[i - 1]) @ res.T[i - 1])
-    return poses, res
+    return compose_chain(odometry[0], res.T), res
+
+
+def compose_chain(pose0, transforms) -> np.ndarray:
+    """Serial SE(2) prefix product of scripts/main.py:249-256:
+    ``pose_i = mat_to_pose(pose_to_mat(pose_{i-1}) @ T_{i-1})``; (n + 1, 3) poses from n transforms.
+    Runs in the library's C host loop (the reference's Python loop costs ~100 ms at n = 5,000)."""
+    T = np.asarray(transforms, dtype=np.float64)
+    T6 = np.ascontiguousarray(T[:, :2, :].reshape(-1, 6))
+    p0 = np.ascontiguousarray(pose0, dtype=np.float64)
+    out = np.empty((len(T6) + 1, 3))
+    _icp._lib.check(_icp._lib.lib().icpb_compose_chain(_icp._ptr(p0), _icp._ptr(T6), len(T6), _icp._ptr(out)),
+                    "icpb_compose_chain")
+    return out
 
 
 def _travelled(xy: np.ndarray) -> np.ndarray:

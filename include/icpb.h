@@ -148,6 +148,11 @@ int icpb_proximity_pairs(icpb_handle h, const double *h_xy, const double *h_trav
                          double min_dist_along_path, double max_dist, int64_t capacity,
                          int32_t *h_pairs, int64_t *n_pairs);
 
+/* Chain composition of the odometry fan-out's results (scripts/main.py:249-256): poses_out has
+ * n + 1 rows (x, y, theta); row 0 is pose0, row i + 1 = mat_to_pose(pose_to_mat(row i) @ T_i).
+ * Pure host function (no handle): a serial dependency chain. */
+int icpb_compose_chain(const double *pose0, const double *T6, int64_t n, double *poses_out);
+
 /* Launch geometry and resource use of the alignment kernel for the current scan table
  * (reported by bench.py next to the roofline numbers). */
 typedef struct icpb_kernel_info {

@@ -79,3 +79,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("no oracle", ""), f
+
+
+def test_compose_chain_matches_reference_loop():
+    """icpb_compose_chain (a host function: runs without a GPU) against the reference's serial
+    composition, restated with the golden SE(2) helpers, and against the end-to-end golden."""
+    from icp_slam_b200 import callers, synth
+    z = np.load(os.path.join(ROOT, "tests", "golden", "slam_golden.npz"))
+    got = callers.compose_chain(z["odometry"][0], z["chain_T"])
+    np.testing.assert_allclose(got, z["corrected"], rtol=0, atol=1e-12)
+    rng = np.random.default_rng(2)
+    T = np.stack([synth.pose_to_mat(p) for p in rng.uniform(-0.3, 0.3, size=(400, 3))])
+    want = np.zeros((401, 3)); want[0] = (1.0, -2.0, 3.0)
+    for i in range(400):
+        want[i + 1] = synth.mat_to_pose(synth.pose_to_mat(want[i]) @ T[i])
+    np.testing.assert_allclose(callers.compose_chain(want[0], T), want, rtol=0, atol=1e-12)
+    assert callers.compose_chain([0, 0, 0], np.zeros((0, 3, 3))).shape == (1, 3)
