@@ -10,14 +10,14 @@ typedef unsigned long long u64;
 
 __device__ __forceinline__ u64 gtime() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-constexpr int NCH = 16;   // independent chains per thread
+constexpr int NCH = 8;   // independent chains per thread
 
 template <int OP>
 __global__ void __launch_bounds__(256) pipes(int iters, float *out, u64 *clk)
 {
-    float a[NCH], b[NCH];
+    float a[NCH], b[NCH], e[NCH], f[NCH];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) { a[k] = threadIdx.x * 0.001f + k; b[k] = 1.0f + k * 1e-3f; }
+    for (int k = 0; k < NCH; ++k) { a[k] = threadIdx.x * 0.001f + k; b[k] = 1.0f + k * 1e-3f; e[k] = a[k] + 2.f; f[k] = b[k] + 3.f; }
     const float c0 = 0.999f + blockIdx.x * 1e-9f, c1 = 1e-3f;
     const u64 t0 = gtime();
     const long long k0 = clock64();
@@ -44,6 +44,16 @@ __global__ void __launch_bounds__(256) pipes(int iters, float *out, u64 *clk)
                 asm("add.f32x2 %0, %0, %1;" : "+l"(v) : "l"(dd));
                 asm("mov.b64 {%0, %1}, %2;" : "=f"(a[k]), "=f"(b[k]) : "l"(v));
             }
+            if (OP == 8 || OP == 9) {                                          // FFMA2 + 1 (or 2) independent scalar FFMA
+                u64 v, cc, dd;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a[k]), "f"(b[k]));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c0));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(c1));
+                asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(cc), "l"(dd));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(a[k]), "=f"(b[k]) : "l"(v));
+                e[k] = __fmaf_rn(e[k], c0, c1);
+                if (OP == 9) f[k] = __fmaf_rn(f[k], c0, c1);
+            }
             if (OP == 7) {                                                     // FFMA + FMNMX3 interleaved 2:1
                 a[k] = __fmaf_rn(a[k], c0, c1);
                 b[k] = __fmaf_rn(b[k], c0, c1);
@@ -55,7 +65,7 @@ __global__ void __launch_bounds__(256) pipes(int iters, float *out, u64 *clk)
     const u64 t1 = gtime();
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) s += a[k] + b[k];
+    for (int k = 0; k < NCH; ++k) s += a[k] + b[k] + e[k] + f[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) { clk[0] = (u64)(k1 - k0); clk[1] = t1 - t0; }
 }
@@ -99,5 +109,7 @@ int main()
     run<5>("FFMA2", NCH, sms, out, clk);
     run<6>("FADD2", NCH, sms, out, clk);
     run<7>("2FFMA+.5FMNMX3", 2.5 * NCH, sms, out, clk);
+    run<8>("FFMA2+1FFMA", 2 * NCH, sms, out, clk);
+    run<9>("FFMA2+2FFMA", 3 * NCH, sms, out, clk);
     return 0;
 }
