@@ -36,8 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 4,999-pair chain, from the
-# committed `ncu --set full` capture (profiles/r01h_align_ncu_full_summary.csv); None until measured
-TRAFFIC_NCU = 88.9e6   # 81.3 MB read (= one pass over the 81 MB scan table) + 7.6 MB written
+# committed `ncu --set full` capture (profiles/r01i_align_ncu_full_summary.csv); None until measured
+TRAFFIC_NCU = 84.3e6   # 81.1 MB read (= one pass over the 81 MB scan table) + 3.2 MB written
 METRIC = "icp_scan_pair_alignments_per_sec"
 UNIT = "pairs/s"
 SEED = 467002
@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--workload", default="chain", choices=["chain", "proximity", "allpairs", "highres"])
     ap.add_argument("--pairs", type=int, default=0, help="cap on the pair count of the non-chain workloads")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU sample")
+    ap.add_argument("--exhaustive", action="store_true", help="run the timed steps with pruning off (profiling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     return ap.parse_args()
@@ -256,7 +257,8 @@ def main():
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device=dev)     # 768 MB > 126 MB L2
 
     def step_device():
-        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
+        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
+                       exhaustive=args.exhaustive)
         if world > 1:
             rec[:, :6] = out_T
             rec[:, 6] = out_err
@@ -285,7 +287,8 @@ def main():
         if world > 1:
             dist.barrier()
         ev[k][0].record()
-        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
+        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
+                       exhaustive=args.exhaustive)
         ev[k][1].record()
         if world > 1:
             rec[:, :6] = out_T
@@ -402,7 +405,7 @@ def main():
         line = {
             "metric": METRIC, "value": world * B * args.steps / total_s, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 filter + f64 decide/accumulate",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"{args.label}, {B} pairs per GPU per step",
                        "pairs_per_step": world * B, "epsilon": 0.05, "max_iters": 100,
