@@ -89,6 +89,9 @@ struct icpb_ctx {
     cudaStream_t cstream[2] = {nullptr, nullptr};   // compute streams of the pipelined host entry point
     cudaEvent_t seg_ev[16] = {};                    // "scan segment k has arrived"
     cudaEvent_t done_ev[2] = {};
+    int32_t *arrived_dev = nullptr;                 // streaming upload: segments delivered so far
+    int32_t *seg_vals_pinned = nullptr;             // 1..17 in pinned host memory (sources of the flag copies)
+    DevBuf s_seg;
     int max_smem_set = 0;
 };
 
@@ -164,7 +167,8 @@ int check_params(const icpb_params *p, int64_t B)
 int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scans, int64_t longest,
            const int32_t *d_pairs, const double *d_init, int64_t B, const icpb_params *p,
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
-           cudaStream_t stream, int64_t B_total = 0)
+           cudaStream_t stream, int64_t B_total = 0, const int32_t *d_seg_of_pair = nullptr,
+           const int32_t *d_arrived = nullptr)
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
@@ -180,6 +184,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.queue = h->queue + (h->launches % kQueueRing);
     a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
     a.executed = h->executed;
+    a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived;
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
     if (grid > B) grid = B;
@@ -244,6 +249,9 @@ int icpb_create(int device, icpb_handle *out)
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&h->cstream[k], cudaStreamNonBlocking);
     for (int k = 0; k < 16 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->seg_ev[k], cudaEventDisableTiming);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->done_ev[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&h->arrived_dev, sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->seg_vals_pinned, sizeof(int32_t) * 32, cudaHostAllocDefault);
+    if (e == cudaSuccess) for (int k = 0; k < 32; ++k) h->seg_vals_pinned[k] = k;
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "icpb_create: %s", cudaGetErrorString(e));
         if (h->queue) cudaFree(h->queue);
@@ -262,6 +270,9 @@ int icpb_destroy(icpb_handle h)
     for (int k = 0; k < 2; ++k) if (h->cstream[k]) { cudaStreamSynchronize(h->cstream[k]); cudaStreamDestroy(h->cstream[k]); }
     for (int k = 0; k < 16; ++k) if (h->seg_ev[k]) cudaEventDestroy(h->seg_ev[k]);
     for (int k = 0; k < 2; ++k) if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
+    if (h->arrived_dev) cudaFree(h->arrived_dev);
+    if (h->seg_vals_pinned) cudaFreeHost(h->seg_vals_pinned);
+    h->s_seg.release();
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -427,8 +438,8 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
     }
     // segments of roughly equal size: enough of them that the first kernels start early, few
     // enough that every group still fills the GPU (a group of a few hundred pairs would not)
-    int nseg = (int)(nb_xy / (16u << 20)) + 1;
-    if (nseg > 4) nseg = 4;                                  // measured best on the 81 MB / 4,999-pair chain
+    int nseg = (int)(nb_xy / (4u << 20)) + 1;                // ~4 MB pieces: the first pairs start after ~0.1 ms
+    if (nseg > 16) nseg = 16;
     if (const char *t = getenv("ICPB_SEGMENTS")) {          // tuning experiments only
         const int v = atoi(t);
         if (v >= 1 && v <= 16) nseg = v;
@@ -471,32 +482,35 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
     if ((rc = h->s_T.reserve(nbI))) return rc;
     if ((rc = h->s_err.reserve(sizeof(double) * (size_t)B))) return rc;
     if ((rc = h->s_passes.reserve(sizeof(int32_t) * (size_t)B))) return rc;
-    cudaStream_t cp = h->stream;
+    cudaStream_t cp = h->stream, cs = h->cstream[0];
+    std::vector<int32_t> pseg((size_t)B);
+    for (int64_t q = 0; q < B; ++q) pseg[q] = seg_of_pair[perm[q]];
+    if ((rc = h->s_seg.reserve(sizeof(int32_t) * (size_t)B))) return rc;
+    CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
     CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
     CU(cudaMemcpyAsync(h->s_pairs.p, ppairs.data(), nbP, cudaMemcpyHostToDevice, cp));
+    CU(cudaMemcpyAsync(h->s_seg.p, pseg.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, cp));
     if (h_init) CU(cudaMemcpyAsync(h->s_init.p, pinit.data(), nbI, cudaMemcpyHostToDevice, cp));
+    CU(cudaEventRecord(h->seg_ev[0], cp));
+    // ONE launch over all pairs, in arrival order; its CTAs wait on the segment counter
+    CU(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
+    rc = launch(h, h->xy, h->offsets, n_scans, longest, (const int32_t *)h->s_pairs.p,
+                h_init ? (const double *)h->s_init.p : nullptr, B, p,
+                (double *)h->s_T.p, (double *)h->s_err.p, (int32_t *)h->s_passes.p,
+                nullptr, nullptr, cs, B, (const int32_t *)h->s_seg.p, h->arrived_dev);
+    if (rc) return rc;
     int64_t s_prev = 0;
     for (int k = 0; k < nseg; ++k) {
         const int64_t o0 = h_offsets[s_prev], o1 = h_offsets[seg_end[k]];
         if (o1 > o0)
             CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
                                cudaMemcpyHostToDevice, cp));
-        CU(cudaEventRecord(h->seg_ev[k], cp));
+        // stream order: the flag lands after the segment it announces
+        CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
         s_prev = seg_end[k];
-        const int64_t b0 = start[k], nb = start[k + 1] - start[k];
-        if (nb == 0) continue;
-        cudaStream_t cs = h->cstream[k & 1];
-        CU(cudaStreamWaitEvent(cs, h->seg_ev[k], 0));
-        rc = launch(h, h->xy, h->offsets, n_scans, longest, (const int32_t *)h->s_pairs.p + 2 * b0,
-                    h_init ? (const double *)h->s_init.p + 6 * b0 : nullptr, nb, p,
-                    (double *)h->s_T.p + 6 * b0, (double *)h->s_err.p + b0, (int32_t *)h->s_passes.p + b0,
-                    nullptr, nullptr, cs, B);
-        if (rc) return rc;
     }
-    for (int k = 0; k < 2; ++k) {
-        CU(cudaEventRecord(h->done_ev[k], h->cstream[k]));
-        CU(cudaStreamWaitEvent(cp, h->done_ev[k], 0));
-    }
+    CU(cudaEventRecord(h->done_ev[0], cs));
+    CU(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
     std::vector<double> tT((size_t)(6 * B)), tE((size_t)B);
     std::vector<int32_t> tP((size_t)B);
     CU(cudaMemcpyAsync(tT.data(), h->s_T.p, nbI, cudaMemcpyDeviceToHost, cp));

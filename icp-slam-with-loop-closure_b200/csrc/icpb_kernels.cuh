@@ -50,6 +50,10 @@ struct KernelArgs {
     int32_t        nchunk_cap;// chunk bounding circles in shared memory
     int32_t        ntile_cap; // source tiles (32*R points) whose partial sums live in shared memory
     unsigned long long *executed; // optional: += distance evaluations actually executed
+    // streaming upload (icpb_align_host): pair b may start once *arrived > seg_of_pair[b], i.e. the
+    // copy engine has delivered the scan-table segment holding the later of its two scans
+    const int32_t *seg_of_pair;
+    const volatile int32_t *arrived;
 };
 
 // ---- fp32 filter distance: one definition, used by the sweep and by the refine step ----------
@@ -319,6 +323,19 @@ icp_align_kernel(const KernelArgs a)
         sync_all();
         const int64_t pid = s_pid;
         if (pid >= a.B) break;
+        if (a.arrived) {
+            // wait for the copy engine (a DMA on another stream, not another kernel): the queue hands
+            // pairs out in arrival order, so only the CTAs at the front of the upload ever wait
+            if (tid == 0) {
+                const int need = a.seg_of_pair[pid];
+                const long long t0 = clock64();
+                while (*a.arrived <= need) {
+                    __nanosleep(256);
+                    if (clock64() - t0 > (1LL << 33)) break;      // ~4 s: never hang the GPU on a failed copy
+                }
+            }
+            __syncthreads();
+        }
 
         int32_t sid, did;
         if (a.p.pair_mode == 1) {

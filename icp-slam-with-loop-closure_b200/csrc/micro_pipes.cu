@@ -54,6 +54,23 @@ __global__ void __launch_bounds__(256) pipes(int iters, float *out, u64 *clk)
                 e[k] = __fmaf_rn(e[k], c0, c1);
                 if (OP == 9) f[k] = __fmaf_rn(f[k], c0, c1);
             }
+            if (OP >= 10 && OP <= 13) {
+                // the sweep's packed mix on independent chains: dx=q-p, dy=q-p, t=dx*dx, d=dy*dy+t
+                u64 q, pp, dx, dy, t;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(a[k]), "f"(b[k]));
+                if (OP == 10 || OP == 12 || OP == 13) asm("mov.b64 %0, {%1, %1};" : "=l"(pp) : "f"(c0));   // broadcast scalar operand
+                else asm("mov.b64 %0, {%1, %2};" : "=l"(pp) : "f"(e[k]), "f"(f[k]));     // two distinct halves
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(q), "l"(pp));
+                if (OP >= 12) {
+                    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(q), "l"(pp));
+                    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dx));
+                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dx) : "l"(dy), "l"(t));
+                }
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(dx));
+                if (OP == 13) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(e[k]) : "f"(lo), "f"(hi)); }
+                else { a[k] = lo; b[k] = hi; }
+            }
             if (OP == 7) {                                                     // FFMA + FMNMX3 interleaved 2:1
                 a[k] = __fmaf_rn(a[k], c0, c1);
                 b[k] = __fmaf_rn(b[k], c0, c1);
@@ -109,6 +126,10 @@ int main()
     run<5>("FFMA2", NCH, sms, out, clk);
     run<6>("FADD2", NCH, sms, out, clk);
     run<7>("2FFMA+.5FMNMX3", 2.5 * NCH, sms, out, clk);
+    run<10>("FADD2 bcast", NCH, sms, out, clk);
+    run<11>("FADD2 full", NCH, sms, out, clk);
+    run<12>("2FADD2+FMUL2+FFMA2", 4 * NCH, sms, out, clk);
+    run<13>("..+FMNMX3", 5 * NCH, sms, out, clk);
     run<8>("FFMA2+1FFMA", 2 * NCH, sms, out, clk);
     run<9>("FFMA2+2FFMA", 3 * NCH, sms, out, clk);
     return 0;

@@ -31,7 +31,7 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f3
 
 __device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-template <int MODE, int R, int CH>
+template <int MODE, int R, int CH, int VAR = 0>
 __global__ void __launch_bounds__(256) sweep(const float *gx, const float *gy, int n2, int reps, float *out)
 {
     extern __shared__ __align__(16) float sm[];
@@ -112,14 +112,42 @@ __global__ void __launch_bounds__(256) sweep(const float *gx, const float *gy, i
                         unpack2(db, d[4 * v + 2], d[4 * v + 3]);
                     }
                 }
-                float cm = d[0];
+                if (VAR == 2) {          // no min at all: fold the distances with packed adds
+                    float sacc = 0.f;
 #pragma unroll
-                for (int k = 1; k + 1 < CH; k += 2) cm = min3f(cm, d[k], d[k + 1]);
-                cm = fminf(cm, d[CH - 1]);
-                const bool better = cm < m1[r];
-                m2[r] = fminf(m2[r], better ? m1[r] : cm);
-                m1[r] = fminf(m1[r], cm);
-                c1[r] = better ? c : c1[r];
+                    for (int k = 0; k < CH; k += 4) sacc += (d[k] + d[k + 1]) + (d[k + 2] + d[k + 3]);
+                    m1[r] += sacc;
+                } else if (VAR == 3) {   // balanced min tree instead of a chain
+                    float t[CH / 2];
+#pragma unroll
+                    for (int k = 0; k < CH / 2; ++k) t[k] = fminf(d[2 * k], d[2 * k + 1]);
+                    float cm = min3f(min3f(t[0], t[1], t[2]), min3f(t[3], t[4], t[5]), fminf(t[6], t[7]));
+                    const bool better = cm < m1[r];
+                    m2[r] = fminf(m2[r], better ? m1[r] : cm);
+                    m1[r] = fminf(m1[r], cm);
+                    c1[r] = better ? c : c1[r];
+                } else {
+                    float cm;
+                    if (VAR == 4) {      // two independent min3 chains
+                        float ca = min3f(d[0], d[1], d[2]), cb2 = min3f(d[3], d[4], d[5]);
+                        ca = min3f(ca, d[6], d[7]); cb2 = min3f(cb2, d[8], d[9]);
+                        ca = min3f(ca, d[10], d[11]); cb2 = min3f(cb2, d[12], d[13]);
+                        cm = min3f(ca, cb2, fminf(d[14], d[15]));
+                    } else {
+                        cm = d[0];
+#pragma unroll
+                        for (int k = 1; k + 1 < CH; k += 2) cm = min3f(cm, d[k], d[k + 1]);
+                        cm = fminf(cm, d[CH - 1]);
+                    }
+                    if (VAR == 1) {      // min only, no bookkeeping
+                        m1[r] = fminf(m1[r], cm);
+                    } else {
+                        const bool better = cm < m1[r];
+                        m2[r] = fminf(m2[r], better ? m1[r] : cm);
+                        m1[r] = fminf(m1[r], cm);
+                        c1[r] = better ? c : c1[r];
+                    }
+                }
             }
         }
 #pragma unroll
@@ -128,26 +156,26 @@ __global__ void __launch_bounds__(256) sweep(const float *gx, const float *gy, i
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
-template <int MODE, int R, int CH>
+template <int MODE, int R, int CH, int VAR = 0>
 void run(const char *name, const float *gx, const float *gy, int n2, int sms, float *out, int threads)
 {
     const int smem = 3 * n2 * sizeof(float);
-    CK(cudaFuncSetAttribute(sweep<MODE, R, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(sweep<MODE, R, CH, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep<MODE, R, CH>, threads, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep<MODE, R, CH, VAR>, threads, smem));
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, sweep<MODE, R, CH>));
+    CK(cudaFuncGetAttributes(&fa, sweep<MODE, R, CH, VAR>));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int per_sm = 1; per_sm <= occ && per_sm <= 8; per_sm *= 2) {
         const int grid = sms * per_sm;
         const int reps = 64;
-        sweep<MODE, R, CH><<<grid, threads, smem>>>(gx, gy, n2, 4, out);
+        sweep<MODE, R, CH, VAR><<<grid, threads, smem>>>(gx, gy, n2, 4, out);
         CK(cudaDeviceSynchronize());
         float best = 1e30f;
         for (int t = 0; t < 3; ++t) {
             CK(cudaEventRecord(e0));
-            sweep<MODE, R, CH><<<grid, threads, smem>>>(gx, gy, n2, reps, out);
+            sweep<MODE, R, CH, VAR><<<grid, threads, smem>>>(gx, gy, n2, reps, out);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -187,5 +215,13 @@ int main(int argc, char **argv)
     if (only < 0 || only == 10) run<3, 4, 16>("expanded packed f32x2", gx, gy, n2, sms, out, 256);
     if (only < 0 || only == 11) run<3, 8, 16>("expanded packed f32x2", gx, gy, n2, sms, out, 128);
     if (only < 0 || only == 12) run<3, 8, 32>("expanded packed f32x2", gx, gy, n2, sms, out, 128);
+    if (only < 0 || only == 20) run<1, 2, 16, 0>("diffp R2 base", gx, gy, n2, sms, out, 128);
+    if (only < 0 || only == 21) run<1, 2, 16, 1>("diffp R2 min only", gx, gy, n2, sms, out, 128);
+    if (only < 0 || only == 22) run<1, 2, 16, 2>("diffp R2 no min", gx, gy, n2, sms, out, 128);
+    if (only < 0 || only == 23) run<1, 2, 16, 3>("diffp R2 tree", gx, gy, n2, sms, out, 128);
+    if (only < 0 || only == 24) run<1, 2, 16, 4>("diffp R2 2chains", gx, gy, n2, sms, out, 128);
+    if (only < 0 || only == 25) run<1, 4, 16, 4>("diffp R4 2chains", gx, gy, n2, sms, out, 256);
+    if (only < 0 || only == 26) run<1, 4, 16, 1>("diffp R4 min only", gx, gy, n2, sms, out, 256);
+    if (only < 0 || only == 27) run<1, 4, 16, 2>("diffp R4 no min", gx, gy, n2, sms, out, 256);
     return 0;
 }
