@@ -361,3 +361,85 @@ def test_cluster_latency_mode_bit_identical(gicp, n_beams, cluster):
     np.testing.assert_array_equal(a.correspondences, b.correspondences)
     np.testing.assert_array_equal(a.T[:1], c.T)
     e.close()
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e4, 0.0), (1e-6, 0.0), (1.0, 3.0e4), (1.0, -2.5e6), (1e-3, 7.0)])
+def test_adversarial_coordinates(gicp, c_oracle, scale, offset):
+    """Coordinates far from the origin / very large / very small: fp32 loses most of its digits,
+    so the filter admits many candidates and the fp64 decision has to do the work -- the
+    correspondences must still be the oracle's, index for index."""
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(int(abs(offset)) % 1000 + int(scale * 10) % 97)
+    poses = synth.loop_trajectory(3, step=0.07)
+    s0, s1, s2 = synth.scans_from_poses(poses, 512, rng, drop_frac=0.03)
+    shift = np.array([offset, -0.5 * offset])
+    scans = [(s * scale + shift) for s in (s0, s1, s2)]
+    pairs = np.array([(1, 0), (2, 1), (2, 0)], dtype=np.int32)
+    eps = 0.05 * scale * scale
+    res = gicp.icp_batch(scans, pairs, None, epsilon=eps, stopping_thresh=1e-4 * scale * scale, max_iters=30,
+                         return_correspondences=True)
+    for b, (s, d) in enumerate(pairs):
+        T, err, passes, corr = c_oracle.icp_pair(scans[s], scans[d], None, epsilon=eps,
+                                                 stopping_thresh=1e-4 * scale * scale, max_iters=30)
+        assert res.iters[b] == passes
+        np.testing.assert_array_equal(res.correspondences[b, :len(corr)], corr)
+        np.testing.assert_allclose(res.error[b], err, rtol=1e-7)
+        np.testing.assert_allclose(res.T[b][:2, :2], T[:2, :2], atol=1e-9)
+        np.testing.assert_allclose(res.T[b][:2, 2], T[:2, 2], atol=1e-9 * max(scale, 1.0) * max(abs(offset), 1.0))
+
+
+def test_duplicates_and_collinear_targets(gicp, c_oracle):
+    """Repeated points, targets on a regular lattice line (equal spacing -> equidistant pairs at
+    chunk boundaries), and a source that sits exactly on targets."""
+    rng = np.random.default_rng(31)
+    line = np.stack((np.arange(200) * 0.125, np.zeros(200)), axis=1)          # exactly representable
+    dst = np.concatenate((line, line[::7], line[:16] + [0.0, 0.25]))
+    src = np.concatenate((line[5:150] + [0.0625, 0.0], line[20:60], dst[200:220]))   # midpoints -> exact ties
+    res = gicp.icp_batch([src, dst], np.array([[0, 1]]), None, epsilon=0.0, stopping_thresh=0.0, max_iters=6,
+                         return_correspondences=True, return_history=True)
+    T, err, passes, corr, hist = c_oracle.icp_pair(src, dst, None, epsilon=0.0, stopping_thresh=0.0, max_iters=6,
+                                                   want_history=True)
+    assert res.iters[0] == passes == 8
+    np.testing.assert_array_equal(res.correspondences[0, :len(corr)], corr)
+    np.testing.assert_allclose(res.history[0, :passes], hist, atol=1e-9)
+    # first pass alone: brute force with numpy's own argmin (first index on exact ties)
+    Tn, c1, e1 = gicp.icp_iteration(hom(src), hom(dst), np.eye(3))
+    d = ((dst[None, :, :] - src[:, None, :]) ** 2).sum(-1)
+    np.testing.assert_array_equal(c1, np.argmin(d, axis=1))
+
+
+def test_random_problem_fuzz(gicp, c_oracle):
+    """Seeded fuzz over sizes, motions and stop parameters (mixed lengths in one scan table)."""
+    rng = np.random.default_rng(2024)
+    scans, pairs, inits = [], [], []
+    for k in range(40):
+        n2 = int(rng.integers(1, 700))
+        n1 = int(rng.integers(1, 700))
+        kind = k % 3
+        if kind == 0:                                           # noisy subset under a small motion
+            dst = rng.uniform(-9, 9, size=(n2, 2))
+            src = dst[rng.integers(0, n2, n1)] + rng.normal(0, 0.03, size=(n1, 2))
+        elif kind == 1:                                         # unrelated clouds
+            dst = rng.normal(0, 4, size=(n2, 2)); src = rng.normal(1, 3, size=(n1, 2))
+        else:                                                   # points on a polyline (scan-like)
+            t = np.sort(rng.uniform(0, 20, n2)); dst = np.stack((t, np.sin(t) + 0.3 * np.floor(t)), axis=1)
+            u = np.sort(rng.uniform(0, 20, n1)); src = np.stack((u, np.sin(u) + 0.3 * np.floor(u)), axis=1) + 0.05
+        th = rng.uniform(-0.2, 0.2)
+        inits.append(np.array([[np.cos(th), -np.sin(th), rng.uniform(-0.3, 0.3)],
+                               [np.sin(th), np.cos(th), rng.uniform(-0.3, 0.3)], [0, 0, 1.0]]))
+        scans += [src, dst]
+        pairs.append((2 * k, 2 * k + 1))
+    pairs = np.array(pairs, dtype=np.int32)
+    inits = np.stack(inits)
+    for kw in (dict(epsilon=0.01, max_iters=40), dict(epsilon=0.0, stopping_thresh=1e-9, max_iters=15),
+               dict(epsilon=0.05, max_iters=25, rotation_only=True)):
+        res = gicp.icp_batch(scans, pairs, inits, return_correspondences=True, **kw)
+        xy, off = c_oracle.pack(scans)
+        T, err, passes = c_oracle.icp_batch(xy, off, pairs, inits, **kw)
+        np.testing.assert_array_equal(res.iters, passes)
+        np.testing.assert_allclose(res.error, err, rtol=1e-8, atol=1e-18)
+        for b, (s, d) in enumerate(pairs):
+            _, _, _, corr = c_oracle.icp_pair(scans[s], scans[d], inits[b], **kw)
+            np.testing.assert_array_equal(res.correspondences[b, :len(corr)], corr)
+            if len(set(corr.tolist())) >= 2:
+                np.testing.assert_allclose(res.T[b], T[b], atol=1e-8)
