@@ -253,10 +253,28 @@ def main():
     out_T = torch.empty((B, 6), dtype=torch.float64, device=dev)
     out_err = torch.empty(B, dtype=torch.float64, device=dev)
     out_pass = torch.empty(B, dtype=torch.int32, device=dev)
-    gathered = torch.empty((world * B, 8), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered, symm = None, None
+    if world > 1:
+        # Preferred: the gather is fused into the alignment kernel -- every finished pair stores its
+        # record into every rank's buffer over NVLink peer memory (torch symmetric memory supplies
+        # the peer mappings and the cross-rank barrier).  Fallback: NCCL all_gather after the kernel.
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            gathered = symm_mem.empty((world * B, 8), dtype=torch.float64, device=dev)
+            symm = symm_mem.rendezvous(gathered, dist.group.WORLD)
+            peer_ptrs_dev = int(symm.buffer_ptrs_dev)
+        except Exception as exc:                          # noqa: BLE001
+            print(f"[rank {rank}] symmetric memory unavailable ({exc}); using NCCL all_gather", file=sys.stderr)
+            symm = None
+            gathered = torch.empty((world * B, 8), dtype=torch.float64, device=dev)
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device=dev)     # 768 MB > 126 MB L2
 
-    def step_device():
+    def align_and_gather():
+        if world > 1 and symm is not None:
+            eng.run_device_gather(pairs_t, init_t, out_T, out_err, out_pass, peer_ptrs_dev, world, rank * B,
+                                  epsilon=0.05, max_iters=100)
+            symm.barrier()                                # all ranks' records have landed everywhere
+            return
         eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
                        exhaustive=args.exhaustive)
         if world > 1:
@@ -264,6 +282,9 @@ def main():
             rec[:, 6] = out_err
             rec[:, 7] = out_pass.to(torch.float64)
             dist.all_gather_into_tensor(gathered, rec)
+
+    def step_device():
+        align_and_gather()
 
     def barrier():
         if world > 1:
@@ -287,18 +308,22 @@ def main():
         if world > 1:
             dist.barrier()
         ev[k][0].record()
-        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
-                       exhaustive=args.exhaustive)
-        ev[k][1].record()
         if world > 1:
-            rec[:, :6] = out_T
-            rec[:, 6] = out_err
-            rec[:, 7] = out_pass.to(torch.float64)
-            dist.all_gather_into_tensor(gathered, rec)
+            align_and_gather()
+            ev[k][1].record()
+        else:
+            eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
+                           exhaustive=args.exhaustive)
+            ev[k][1].record()
         ev[k][2].record()
     barrier()
     t_wall1 = time.time()
     launches = eng.launch_count - launches0
+    if world > 1:
+        # every rank must hold every rank's records: check this rank's own block and that all blocks are filled
+        mine = gathered[rank * B:(rank + 1) * B]
+        assert torch.equal(mine[:, :6], out_T) and torch.equal(mine[:, 6], out_err)
+        assert bool((gathered[:, 7] >= 1).all()), "a rank's records are missing from the gather buffer"
     step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
     kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
     total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
@@ -338,6 +363,9 @@ def main():
         tab_pin = gicp.ScanTable(xy=xy_pin.numpy(), offsets=off_pin.numpy())
         pairs_h, init_h = pairs_pin.numpy(), init
         eng2 = gicp.IcpEngine(local)
+        e2e_gathered = torch.empty((world * B, 8), dtype=torch.float64, device=dev) if world > 1 else None
+        rec_pin = torch.empty((B, 8), dtype=torch.float64).pin_memory() if world > 1 else None
+        from icp_slam_b200 import dist as gdist
 
         def step_host():
             # the public call: scans + pairs + initial guesses in host memory -> constraints in host memory
@@ -349,9 +377,13 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.steps):
             res = step_host()
-            if world > 1:                        # the gather of constraint records, from host results
-                rec[:, :6].copy_(torch.from_numpy(res.T[:, :2, :].reshape(B, 6)))
-                dist.all_gather_into_tensor(gathered, rec)
+            if world > 1 and not os.environ.get("BENCH_E2E_NOGATHER"):   # the gather of constraint records, from host results
+                rec_pin.copy_(torch.from_numpy(gdist.pack_records(res.T, res.error, res.iters)))
+                rec.copy_(rec_pin, non_blocking=True)
+                dist.all_gather_into_tensor(e2e_gathered, rec)
+                # finish the collective before the next step's kernel (whose CTAs wait on the copy
+                # engine) takes the SMs: kernels of different ranks must never wait on each other
+                torch.cuda.synchronize()
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -410,7 +442,10 @@ def main():
             "config": {"workload": f"{args.label}, {B} pairs per GPU per step",
                        "pairs_per_step": world * B, "epsilon": 0.05, "max_iters": 100,
                        "mean_passes": float(passes.mean()), "l2": "flushed between timed steps (768 MB fill)",
-                       "collective": "all_gather of (B,8) f64 constraint records" if world > 1 else "none",
+                       "collective": ("none" if world == 1 else
+                                      "fused: kernel epilogue stores (B,8) f64 records into every rank's buffer over "
+                                      "NVLink peer memory + symmetric-memory barrier" if symm is not None else
+                                      "NCCL all_gather of (B,8) f64 constraint records"),
                        "kernel": info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,

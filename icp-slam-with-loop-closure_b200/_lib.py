@@ -19,7 +19,8 @@ EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destr
            "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
            "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host",
-           "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain"]
+           "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
+           "icpb_run_device_gather"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -84,6 +85,8 @@ def lib() -> ctypes.CDLL:
     L.icpb_upload_scans.argtypes = [vp, dp, vp, i64]
     L.icpb_set_scans_device.argtypes = [vp, dp, vp, i64, i64]
     L.icpb_run_device.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p, vp]
+    L.icpb_run_device_gather.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, vp,
+                                         ctypes.c_int32, i64, vp]
     L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_align_host.argtypes = [vp, dp, vp, i64, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p]
     L.icpb_proximity_closest.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i32p, dp]

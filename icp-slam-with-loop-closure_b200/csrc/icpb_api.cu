@@ -168,7 +168,8 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
            const int32_t *d_pairs, const double *d_init, int64_t B, const icpb_params *p,
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
            cudaStream_t stream, int64_t B_total = 0, const int32_t *d_seg_of_pair = nullptr,
-           const int32_t *d_arrived = nullptr)
+           const int32_t *d_arrived = nullptr, double *const *d_peers = nullptr, int n_peers = 0,
+           int64_t rec_row0 = 0)
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
@@ -185,6 +186,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
     a.executed = h->executed;
     a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived;
+    a.peers = d_peers; a.n_peers = n_peers; a.rec_row0 = rec_row0;
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
     if (grid > B) grid = B;
@@ -342,6 +344,25 @@ int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init,
     CU(cudaSetDevice(h->device));
     return launch(h, h->xy, h->offsets, h->n_scans, h->longest, d_pairs, d_init, B, p,
                   d_T, d_err, d_passes, d_hist, d_corr, (cudaStream_t)stream);
+}
+
+int icpb_run_device_gather(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
+                           const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
+                           const uint64_t *d_peer_ptrs, int32_t n_peers, int64_t row0, void *stream)
+{
+    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
+    if (B > 0 && (!d_T || !d_err || !d_passes)) return fail(ICPB_EINVAL, "output pointer is null%s");
+    if (B > 0 && p->pair_mode == 0 && !d_pairs) return fail(ICPB_EINVAL, "pairs is null with pair_mode 0%s");
+    if (!d_peer_ptrs || n_peers < 1 || n_peers > 8 || row0 < 0)
+        return fail(ICPB_EINVAL, "icpb_run_device_gather: 1..8 peer buffers expected%s");
+    if (p->hist_cap > 0 || p->corr_stride > 0) return fail(ICPB_EINVAL, "icpb_run_device_gather: no history/correspondences%s");
+    CU(cudaSetDevice(h->device));
+    return launch(h, h->xy, h->offsets, h->n_scans, h->longest, d_pairs, d_init, B, p, d_T, d_err, d_passes,
+                  nullptr, nullptr, (cudaStream_t)stream, 0, nullptr, nullptr,
+                  (double *const *)d_peer_ptrs, n_peers, row0);
 }
 
 static int run_host_common(icpb_handle h, const double *xy, const int64_t *offsets, int64_t n_scans,

@@ -54,6 +54,12 @@ struct KernelArgs {
     // copy engine has delivered the scan-table segment holding the later of its two scans
     const int32_t *seg_of_pair;
     const volatile int32_t *arrived;
+    // fused gather (multi-GPU): every finished pair's 8-double constraint record
+    // [T(6), error, passes] is stored straight into every rank's gather buffer over NVLink peer
+    // memory, at row rec_row0 + pair id; peers[r] is rank r's buffer as mapped in this process
+    double *const *peers;
+    int32_t n_peers;
+    int64_t rec_row0;
 };
 
 // ---- fp32 filter distance: one definition, used by the sweep and by the refine step ----------
@@ -691,6 +697,11 @@ icp_align_kernel(const KernelArgs a)
             for (int k = 0; k < 6; ++k) a.T_out[6 * pid + k] = Tmine[k];
             a.err_out[pid] = err;
             a.passes_out[pid] = passes;
+        }
+        if (a.n_peers > 0 && crank == 0 && tid < 8 * a.n_peers) {
+            const int r = tid >> 3, k = tid & 7;                // 8 lanes per peer: one 64-byte record each
+            const double v = k < 6 ? Tw[k] : (k == 6 ? err : (double)passes);
+            a.peers[r][(a.rec_row0 + pid) * 8 + k] = v;
         }
         if (a.corr) {
             int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;

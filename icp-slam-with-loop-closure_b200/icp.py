@@ -291,6 +291,26 @@ class IcpEngine:
                                            vp(out_passes.data_ptr()), None, None, vp(stream)),
                    "icpb_run_device")
 
+    def run_device_gather(self, pairs_t, init_t, out_T, out_err, out_passes, peer_ptrs_dev: int, n_peers: int,
+                          row0: int, epsilon=0.01, max_iters=100, stopping_thresh=0.0001, rotation_only=False,
+                          stream=None):
+        """`run_device` with the all-gather fused into the kernel: every finished pair's record
+        [T(6), error, passes] is stored into every rank's (total, 8) float64 gather buffer at row
+        row0 + pair id over NVLink peer memory.  `peer_ptrs_dev` is the device address of the array
+        of peer buffer pointers (torch symmetric memory: ``handle.buffer_ptrs_dev``)."""
+        import torch
+        p = _params(epsilon, max_iters, stopping_thresh, rotation_only)
+        B = int(pairs_t.shape[0])
+        p.k_block = max(B, 1)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        vp = ctypes.c_void_p
+        _lib.check(self._L.icpb_run_device_gather(self._h, vp(pairs_t.data_ptr()),
+                                                  vp(init_t.data_ptr()) if init_t is not None else None, B,
+                                                  ctypes.byref(p), vp(out_T.data_ptr()), vp(out_err.data_ptr()),
+                                                  vp(out_passes.data_ptr()), vp(int(peer_ptrs_dev)), int(n_peers),
+                                                  int(row0), vp(stream)), "icpb_run_device_gather")
+
     # -- one pair given as two arrays ------------------------------------------------------------
     def pair(self, src_xy, dst_xy, init6, p: _lib.IcpbParams, want_hist: bool, want_corr: bool):
         src = np.ascontiguousarray(src_xy, dtype=np.float64)

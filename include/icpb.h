@@ -99,6 +99,19 @@ int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init,
                     const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
                     double *d_hist, int32_t *d_corr, void *stream);
 
+/*
+ * Multi-GPU: icpb_run_device with the gather of the constraint records fused into the kernel.
+ * d_peer_ptrs is a device array of n_peers (<= 8) pointers: the gather buffer of every rank
+ * ((total pairs, 8) float64 rows [T(6), error, passes]) as mapped into THIS process (CUDA peer /
+ * symmetric memory).  Each finished pair stores its record into every buffer at row
+ * row0 + pair id, over NVLink, instead of a separate all-gather after the kernel.  The caller
+ * orders the launch before a cross-rank barrier.  Replaces the result gather of the reference's
+ * fan-out, `zip(*parallel(...))` (scripts/main.py:241), across ranks.
+ */
+int icpb_run_device_gather(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
+                           const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
+                           const uint64_t *d_peer_ptrs, int32_t n_peers, int64_t row0, void *stream);
+
 /* Same with host buffers: copies the inputs to the device, runs, copies the results back and
  * synchronises.  This is the call a reference-side binding makes. */
 int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, int64_t B,
