@@ -443,3 +443,31 @@ def test_random_problem_fuzz(gicp, c_oracle):
             np.testing.assert_array_equal(res.correspondences[b, :len(corr)], corr)
             if len(set(corr.tolist())) >= 2:
                 np.testing.assert_allclose(res.T[b], T[b], atol=1e-8)
+
+
+def test_fused_gather_epilogue_single_rank(gicp):
+    """icpb_run_device_gather with this GPU as its own (only) peer: the kernel epilogue must write
+    the [T(6), error, passes] record of every pair at row row0 + pair id of the gather buffer."""
+    import torch
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(30, 360, seed=91)
+    e = gicp.IcpEngine()
+    e.set_scans(scans)
+    ref = e.run(pairs, init, epsilon=0.05)
+    dev = torch.device("cuda", e.device)
+    B, row0 = len(pairs), 7
+    buf = torch.full((B + 10, 8), -1.0, dtype=torch.float64, device=dev)
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=dev)
+    pairs_t = torch.from_numpy(pairs).to(dev)
+    init_t = torch.from_numpy(np.ascontiguousarray(init[:, :2, :].reshape(B, 6))).to(dev)
+    oT = torch.empty((B, 6), dtype=torch.float64, device=dev)
+    oe = torch.empty(B, dtype=torch.float64, device=dev)
+    op = torch.empty(B, dtype=torch.int32, device=dev)
+    e.run_device_gather(pairs_t, init_t, oT, oe, op, ptrs.data_ptr(), 1, row0, epsilon=0.05)
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    np.testing.assert_array_equal(got[row0:row0 + B, :6].reshape(B, 2, 3), ref.T[:, :2, :])
+    np.testing.assert_array_equal(got[row0:row0 + B, 6], ref.error)
+    np.testing.assert_array_equal(got[row0:row0 + B, 7], ref.iters)
+    assert np.all(got[:row0] == -1) and np.all(got[row0 + B:] == -1)
+    e.close()
