@@ -56,6 +56,23 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e)); return (int)e; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct LaunchCfg {
     int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ntile_cap, ctas_per_sm;
     int cluster;   // CTAs per problem (1 = ordinary launch)
@@ -92,6 +109,7 @@ struct icpb_ctx {
     int32_t *arrived_dev = nullptr;                 // streaming upload: segments delivered so far
     int32_t *seg_vals_pinned = nullptr;             // 1..17 in pinned host memory (sources of the flag copies)
     DevBuf s_seg;
+    PinnedBuf stage;                                // pinned staging of the small per-call arrays
     int max_smem_set = 0;
 };
 
@@ -274,7 +292,7 @@ int icpb_destroy(icpb_handle h)
     for (int k = 0; k < 2; ++k) if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
     if (h->arrived_dev) cudaFree(h->arrived_dev);
     if (h->seg_vals_pinned) cudaFreeHost(h->seg_vals_pinned);
-    h->s_seg.release();
+    h->s_seg.release(); h->stage.release();
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -490,28 +508,29 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
     for (int k = 0; k < nseg; ++k) start[k + 1] += start[k];
     std::vector<int64_t> perm((size_t)B), fill(start.begin(), start.end() - 1);
     for (int64_t b = 0; b < B; ++b) perm[fill[seg_of_pair[b]]++] = b;
-    std::vector<int32_t> ppairs((size_t)(2 * B));
-    std::vector<double> pinit(h_init ? (size_t)(6 * B) : 0);
+    const size_t nbP = sizeof(int32_t) * 2 * (size_t)B, nbI = sizeof(double) * 6 * (size_t)B;
+    // pinned staging: [T | init | err | pairs | passes | seg], 8-byte members first
+    if ((rc = h->stage.reserve(2 * nbI + sizeof(double) * (size_t)B + nbP + 2 * sizeof(int32_t) * (size_t)B))) return rc;
+    double *tT = (double *)h->stage.p, *pinit = tT + 6 * B, *tE = pinit + 6 * B;
+    int32_t *ppairs = (int32_t *)(tE + B), *tP = ppairs + 2 * B, *pseg = tP + B;
     for (int64_t q = 0; q < B; ++q) {
         const int64_t b = perm[q];
         ppairs[2 * q] = h_pairs[2 * b]; ppairs[2 * q + 1] = h_pairs[2 * b + 1];
-        if (h_init) memcpy(&pinit[6 * q], h_init + 6 * b, 6 * sizeof(double));
+        pseg[q] = seg_of_pair[b];
+        if (h_init) memcpy(pinit + 6 * q, h_init + 6 * b, 6 * sizeof(double));
     }
-    const size_t nbP = sizeof(int32_t) * 2 * (size_t)B, nbI = sizeof(double) * 6 * (size_t)B;
     if ((rc = h->s_pairs.reserve(nbP))) return rc;
     if (h_init && (rc = h->s_init.reserve(nbI))) return rc;
     if ((rc = h->s_T.reserve(nbI))) return rc;
     if ((rc = h->s_err.reserve(sizeof(double) * (size_t)B))) return rc;
     if ((rc = h->s_passes.reserve(sizeof(int32_t) * (size_t)B))) return rc;
     cudaStream_t cp = h->stream, cs = h->cstream[0];
-    std::vector<int32_t> pseg((size_t)B);
-    for (int64_t q = 0; q < B; ++q) pseg[q] = seg_of_pair[perm[q]];
     if ((rc = h->s_seg.reserve(sizeof(int32_t) * (size_t)B))) return rc;
     CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
     CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
-    CU(cudaMemcpyAsync(h->s_pairs.p, ppairs.data(), nbP, cudaMemcpyHostToDevice, cp));
-    CU(cudaMemcpyAsync(h->s_seg.p, pseg.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, cp));
-    if (h_init) CU(cudaMemcpyAsync(h->s_init.p, pinit.data(), nbI, cudaMemcpyHostToDevice, cp));
+    CU(cudaMemcpyAsync(h->s_pairs.p, ppairs, nbP, cudaMemcpyHostToDevice, cp));
+    CU(cudaMemcpyAsync(h->s_seg.p, pseg, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, cp));
+    if (h_init) CU(cudaMemcpyAsync(h->s_init.p, pinit, nbI, cudaMemcpyHostToDevice, cp));
     CU(cudaEventRecord(h->seg_ev[0], cp));
     // ONE launch over all pairs, in arrival order; its CTAs wait on the segment counter
     CU(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
@@ -532,15 +551,13 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
     }
     CU(cudaEventRecord(h->done_ev[0], cs));
     CU(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
-    std::vector<double> tT((size_t)(6 * B)), tE((size_t)B);
-    std::vector<int32_t> tP((size_t)B);
-    CU(cudaMemcpyAsync(tT.data(), h->s_T.p, nbI, cudaMemcpyDeviceToHost, cp));
-    CU(cudaMemcpyAsync(tE.data(), h->s_err.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, cp));
-    CU(cudaMemcpyAsync(tP.data(), h->s_passes.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, cp));
+    CU(cudaMemcpyAsync(tT, h->s_T.p, nbI, cudaMemcpyDeviceToHost, cp));
+    CU(cudaMemcpyAsync(tE, h->s_err.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, cp));
+    CU(cudaMemcpyAsync(tP, h->s_passes.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, cp));
     CU(cudaStreamSynchronize(cp));
     for (int64_t q = 0; q < B; ++q) {
         const int64_t b = perm[q];
-        memcpy(h_T + 6 * b, &tT[6 * q], 6 * sizeof(double));
+        memcpy(h_T + 6 * b, tT + 6 * q, 6 * sizeof(double));
         h_err[b] = tE[q];
         h_passes[b] = tP[q];
     }
