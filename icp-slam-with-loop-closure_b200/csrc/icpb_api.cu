@@ -79,10 +79,16 @@ struct LaunchCfg {
 };
 
 typedef void (*kernel_fn)(const icpb::KernelArgs);
+// The exhaustive variant (every source point sweeps every target) keeps 4 points per thread in
+// 256-thread CTAs: with no pruning there is nothing to balance, and the wider register tile
+// amortises the shared-memory loads and the per-chunk bookkeeping over twice the distances.
+constexpr int kPointsExhaustive = 4;
+bool is_exhaustive(const icpb_params *p) { return p && (p->flags & ICPB_FLAG_EXHAUSTIVE); }
+int points_per_thread(const icpb_params *p) { return is_exhaustive(p) ? kPointsExhaustive : kPointsPerThread; }
 kernel_fn pick_kernel(const icpb_params *p)
 {
-    return (p && (p->flags & ICPB_FLAG_EXHAUSTIVE)) ? icpb::icp_align_kernel<kPointsPerThread, false, false>
-                                                    : icpb::icp_align_kernel<kPointsPerThread, true, false>;
+    return is_exhaustive(p) ? icpb::icp_align_kernel<kPointsExhaustive, false, false>
+                            : icpb::icp_align_kernel<kPointsPerThread, true, false>;
 }
 kernel_fn cluster_kernel() { return icpb::icp_align_kernel<kPointsPerThread, true, true>; }
 
@@ -115,13 +121,13 @@ struct icpb_ctx {
 
 namespace {
 
-int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn)
+int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn, int R = kPointsPerThread)
 {
     if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
     const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
     const int64_t n1c = (longest + 3) & ~int64_t(3);
     const int64_t nchunk = n2pad / icpb::kChunk;
-    const int64_t ntile = (longest + 32 * kPointsPerThread - 1) / (32 * kPointsPerThread);
+    const int64_t ntile = (longest + 32 * R - 1) / (32 * R);
     const int64_t smem = 8 * n2pad + 16 * nchunk + 4 * n1c + 8 * (2 * ntile * icpb::kNumSums + icpb::kMaxWarps * 6);
     if (smem > kMaxSmem) {
         snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
@@ -132,7 +138,7 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     // Small CTAs keep more independent problems in flight per SM (less idling at the per-pass
     // barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
     // problems per resident CTA (tail) or a single pair (latency).
-    int max_threads = (B >= 2048) ? 128 : 256;
+    int max_threads = (B >= 2048 && R < 4) ? 128 : 256;
     if (const char *t = getenv("ICPB_THREADS")) {         // tuning experiments only
         const int v = atoi(t);
         if (v >= 32 && v <= 256 && v % 32 == 0) max_threads = v;
@@ -158,7 +164,7 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     if ((int)smem > h->max_smem_set) {
         CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, false, false>,
+        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsExhaustive, false, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -192,7 +198,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     if (B == 0) return 0;
     LaunchCfg cfg;
     kernel_fn fn = pick_kernel(p);
-    int rc = make_cfg(h, longest, B_total > B ? B_total : B, &cfg, fn);
+    int rc = make_cfg(h, longest, B_total > B ? B_total : B, &cfg, fn, points_per_thread(p));
     if (rc) return rc;
     icpb::KernelArgs a;
     a.xy = xy; a.offsets = offsets; a.pairs = d_pairs; a.init = d_init; a.B = B; a.n_scans = n_scans;

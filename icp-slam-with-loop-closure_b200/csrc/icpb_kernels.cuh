@@ -282,7 +282,7 @@ template <int R, bool PRUNE, bool CLUSTER>
 #ifndef ICPB_MIN_CTAS
 #define ICPB_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, ICPB_MIN_CTAS)
+__global__ void __launch_bounds__(256, (R >= 4 ? 2 : ICPB_MIN_CTAS))
 icp_align_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
