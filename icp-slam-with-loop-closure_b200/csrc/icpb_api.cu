@@ -127,14 +127,15 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
     const int64_t n1c = (longest + 3) & ~int64_t(3);
     const int64_t nchunk = n2pad / icpb::kChunk;
-    const int64_t ntile = (longest + 32 * R - 1) / (32 * R);
+    const int64_t ntile = (longest + 63) / 64;              // 64-point reduction tiles (independent of R)
+    const int64_t nwork = (ntile + R / 2 - 1) / (R / 2);    // warp work items of 32*R points
     const int64_t smem = 8 * n2pad + 16 * nchunk + 4 * n1c + 8 * (2 * ntile * icpb::kNumSums + icpb::kMaxWarps * 6);
     if (smem > kMaxSmem) {
         snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
                  (long long)longest, (long long)smem, kMaxSmem);
         return ICPB_ETOOLONG;
     }
-    int threads = (int)(ntile * 32);                      // one warp per tile, up to 8 warps
+    int threads = (int)(nwork * 32);                      // one warp per work item, up to 8 warps
     // Small CTAs keep more independent problems in flight per SM (less idling at the per-pass
     // barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
     // problems per resident CTA (tail) or a single pair (latency).
@@ -150,9 +151,9 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     // Latency mode: with fewer problems than SMs and more tiles than one CTA has warps, spread each
     // problem over a thread-block cluster (a power of two, at most 8 CTAs) so every tile gets a warp.
     c->cluster = 1;
-    if (fn == pick_kernel(nullptr) && B * 2 <= h->sm_count && ntile > 8) {
+    if (fn == pick_kernel(nullptr) && B * 2 <= h->sm_count && nwork > 8) {
         int cl = 2;
-        while (cl < 8 && (int64_t)cl * 8 < ntile) cl *= 2;
+        while (cl < 8 && (int64_t)cl * 8 < nwork) cl *= 2;
         while (cl > 1 && B * cl > h->sm_count) cl /= 2;
         c->cluster = cl;
     }

@@ -360,7 +360,12 @@ icp_align_kernel(const KernelArgs a)
         const int n2pad = (n2 + kChunk - 1) / kChunk * kChunk;
         const int nchunks = n2pad / kChunk;
         const double inv_n = 1.0 / (double)n1;
-        const int ntiles = (n1 + 32 * R - 1) / (32 * R);
+        // reduction tiles are always 64 points (32 lanes x 2), whatever R: a warp work item covers
+        // SUBT = R/2 consecutive reduction tiles, so kernels with different R add in the same order
+        constexpr int SUBT = R / 2;
+        static_assert(R % 2 == 0, "R must be even");
+        const int ntiles = (n1 + 63) / 64;                 // reduction tiles
+        const int nwork = (ntiles + SUBT - 1) / SUBT;            // warp work items
 
         // ---------------- stage the target in shared memory as fp32 SoA ----------------
         {
@@ -412,9 +417,10 @@ icp_align_kernel(const KernelArgs a)
                 int tile = 0;
                 if (lane == 0) tile = atomicAdd(&s_tile_ctr[passes & 1], 1);
                 tile = __shfl_sync(0xffffffffu, tile, 0);
-                if (CLUSTER) tile = crank + tile * csize;        // this CTA owns tiles crank, crank + csize, ...
-                if (tile >= ntiles) break;
-                const int i0 = (tile * 32 + lane) * R;
+                if (CLUSTER) tile = crank + tile * csize;        // this CTA owns items crank, crank + csize, ...
+                if (tile >= nwork) break;
+                // point r of this lane: reduction tile tile*SUBT + r/2, lane's pair of consecutive points
+                auto pidx = [&](int r) { return ((tile * SUBT + (r >> 1)) * 32 + lane) * 2 + (r & 1); };
                 // ---- transform, upper bounds, tile bounding circle ----
                 float px[R], py[R];
                 float ubmax = 0.0f, lx = kInf, ly = kInf, hx = -kInf, hy = -kInf;
@@ -424,7 +430,7 @@ icp_align_kernel(const KernelArgs a)
                     for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const int i = min(i0 + r, n1 - 1);       // lanes past the end repeat the last point
+                        const int i = min(pidx(r), n1 - 1);      // lanes past the end repeat the last point
                         const double2 s = src[i];
                         double X, Y;
                         apply_T(T, s.x, s.y, X, Y);
@@ -452,7 +458,7 @@ icp_align_kernel(const KernelArgs a)
                     if (passes > 0) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const int j = corr_s[min(i0 + r, n1 - 1)];
+                            const int j = corr_s[min(pidx(r), n1 - 1)];
                             ub[r] = dist32(px[r], py[r], tqx[j], tqy[j]);
                         }
                     } else {
@@ -547,9 +553,6 @@ icp_align_kernel(const KernelArgs a)
                     }
                 }
                 // ---- exact decision among the filter's candidates, then the fit sums ----
-                double sum[kNumSums];
-#pragma unroll
-                for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
                 {
                     double T[6];
 #pragma unroll
@@ -557,8 +560,14 @@ icp_align_kernel(const KernelArgs a)
                     double cx, cy;                               // shift = transformed first source point
                     apply_T(T, s0.x, s0.y, cx, cy);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int i = i0 + r;
+                    for (int sub = 0; sub < SUBT; ++sub) {
+                    double sum[kNumSums];
+#pragma unroll
+                    for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int r = sub * 2 + rr;
+                        const int i = pidx(r);
                         if (i < n1) {
                             const double2 s = src[i];
                             double Px, Py;
@@ -601,14 +610,16 @@ icp_align_kernel(const KernelArgs a)
                             sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
                         }
                     }
-                }
-                {
-                    const double (&s8)[8] = reinterpret_cast<const double (&)[8]>(sum);
-                    const double tot = warp_sum8(s8, lane);                // sums 0..7, see warp_sum8
-                    const double e8 = warp_sum(sum[8]);
-                    if ((lane & 3) == 0)
-                        redp[tile * kNumSums + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
-                    if (lane == 1) redp[tile * kNumSums + 8] = e8;
+                    const int rt = tile * SUBT + sub;                           // reduction tile
+                    if (rt < ntiles) {                                       // warp-uniform
+                        const double (&s8)[8] = reinterpret_cast<const double (&)[8]>(sum);
+                        const double tot = warp_sum8(s8, lane);              // sums 0..7, see warp_sum8
+                        const double e8 = warp_sum(sum[8]);
+                        if ((lane & 3) == 0)
+                            redp[rt * kNumSums + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
+                        if (lane == 1) redp[rt * kNumSums + 8] = e8;
+                    }
+                    }
                 }
             }
 
@@ -627,7 +638,7 @@ icp_align_kernel(const KernelArgs a)
                     } else {                                     // tile t lives in CTA t mod csize
                         cg::cluster_group cluster = cg::this_cluster();
                         for (int t = lane / kNumSums; t < ntiles; t += 3)
-                            col += cluster.map_shared_rank(redp, t % csize)[t * kNumSums + k];
+                            col += cluster.map_shared_rank(redp, (t / SUBT) % csize)[t * kNumSums + k];
                     }
                 }
 #pragma unroll
@@ -707,7 +718,7 @@ icp_align_kernel(const KernelArgs a)
             int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;
             const int lim = min(n1, a.p.corr_stride);
             for (int i = tid; i < lim; i += NT)
-                if (!CLUSTER || (i / (32 * R)) % csize == crank) crow[i] = corr_s[i];   // own tiles only
+                if (!CLUSTER || (i / (32 * R)) % csize == crank) crow[i] = corr_s[i];   // own work items only
         }
         sync_all();             // smem is reused by the next problem (remote reads of red included)
     }
