@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 4,999-pair chain, from the
-# committed `ncu --set full` capture (profiles/r01i_align_ncu_full_summary.csv); None until measured
+# committed `ncu --set full` capture (profiles/r01j_align_ncu_full_summary.csv); None until measured
 TRAFFIC_NCU = 84.3e6   # 81.1 MB read (= one pass over the 81 MB scan table) + 3.2 MB written
 METRIC = "icp_scan_pair_alignments_per_sec"
 UNIT = "pairs/s"
