@@ -95,6 +95,16 @@ def main():
     tR = np.array([[np.cos(tth), -np.sin(tth)], [np.sin(tth), np.cos(tth)]])
     cases.append(run_case("toy20", toy, toy @ tR.T + rng.uniform(0, 1, size=2), np.eye(3)))
 
+    # full-resolution pairs of the headline workload (1,024 beams): a chain pair with its odometry
+    # guess and a loop-closure-like pair from the identity
+    scans1k, pairs1k, init1k, _, _ = synth.make_chain_workload(6, 1024, seed=467002, drop_frac=0.03)
+    cases.append(run_case("chain1024_2", scans1k[3], scans1k[2], init1k[2], max_iters=100, epsilon=0.05))
+    pa = base[40]
+    pb = pa + np.array([0.35, -0.25, 0.12])
+    sa = synth.scans_from_poses(pa[None], 1024, rng, drop_frac=0.02)[0]
+    sb = synth.scans_from_poses(pb[None], 1024, rng, drop_frac=0.02)[0]
+    cases.append(run_case("loop1024", sb, sa, np.eye(3), max_iters=100, epsilon=0.05))
+
     out = {}
     for c in cases:
         for key, val in c.items():

@@ -95,3 +95,25 @@ def test_compose_chain_matches_reference_loop():
         want[i + 1] = synth.mat_to_pose(synth.pose_to_mat(want[i]) @ T[i])
     np.testing.assert_allclose(callers.compose_chain(want[0], T), want, rtol=0, atol=1e-12)
     assert callers.compose_chain([0, 0, 0], np.zeros((0, 3, 3))).shape == (1, 3)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (runs on host cores, no GPU needed) prints ONE JSON line with the
+    contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--scans", "40", "--beams", "128"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
+    assert "workload" in d["config"]
