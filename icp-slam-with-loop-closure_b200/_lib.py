@@ -20,7 +20,7 @@ EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destr
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
            "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host",
            "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
-           "icpb_run_device_gather"]
+           "icpb_run_device_gather", "icpb_pose_graph_sgd"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -48,6 +48,7 @@ def sources():
     c = os.path.join(_HERE, "csrc")
     return [os.path.join(c, "icpb_api.cu")], [os.path.join(c, "icpb_kernels.cuh"),
                                               os.path.join(c, "icpb_candidates.cuh"),
+                                              os.path.join(c, "icpb_sgd.cuh"),
                                               os.path.join(_ROOT, "include", "icpb.h")]
 
 
@@ -93,6 +94,7 @@ def lib() -> ctypes.CDLL:
     L.icpb_proximity_pairs.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i64, i32p,
                                        ctypes.POINTER(ctypes.c_int64)]
     L.icpb_compose_chain.argtypes = [dp, dp, i64, dp]
+    L.icpb_pose_graph_sgd.argtypes = [vp, dp, i64, i32p, dp, i64, dp, ctypes.c_int32, ctypes.c_double]
     L.icpb_fit_pairs_host.argtypes = [vp, dp, dp, i64, dp, dp]
     L.icpb_icp_pair_host.argtypes = [vp, dp, i64, dp, i64, dp, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_get_kernel_info.argtypes = [vp, i64, ctypes.POINTER(IcpbKernelInfo)]

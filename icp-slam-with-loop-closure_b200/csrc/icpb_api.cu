@@ -12,6 +12,7 @@
 #include "icpb.h"
 #include "icpb_kernels.cuh"
 #include "icpb_candidates.cuh"
+#include "icpb_sgd.cuh"
 
 namespace {
 
@@ -116,6 +117,7 @@ struct icpb_ctx {
     int32_t *seg_vals_pinned = nullptr;             // 1..17 in pinned host memory (sources of the flag copies)
     DevBuf s_seg;
     PinnedBuf stage;                                // pinned staging of the small per-call arrays
+    DevBuf s_sgd;                                   // pose-graph SGD: poses, edges, transforms, scratch
     int max_smem_set = 0;
 };
 
@@ -299,7 +301,7 @@ int icpb_destroy(icpb_handle h)
     for (int k = 0; k < 2; ++k) if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
     if (h->arrived_dev) cudaFree(h->arrived_dev);
     if (h->seg_vals_pinned) cudaFreeHost(h->seg_vals_pinned);
-    h->s_seg.release(); h->stage.release();
+    h->s_seg.release(); h->stage.release(); h->s_sgd.release();
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -717,6 +719,81 @@ int icpb_compose_chain(const double *pose0, const double *T6, int64_t n, double 
         double *q = poses_out + 3 * (i + 1);
         q[0] = x; q[1] = y; q[2] = atan2(m10, m00);
     }
+    return 0;
+}
+
+/* Pose-graph SGD (include/icpb.h): n_steps passes of the reference's
+ * pose_graph_optimization_step_sgd over the same edge list, poses updated in place. */
+int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t *h_edges,
+                        const double *h_edge_T6, int64_t n_edges, const double *h_learning_rates,
+                        int32_t n_steps, double loop_closure_uncertainty)
+{
+    if (!h || !h_poses || n <= 0 || n > 0x1fffffff || n_edges < 0 || n_edges > 0x1fffffff || n_steps < 0 ||
+        (n_edges > 0 && (!h_edges || !h_edge_T6)) || (n_steps > 0 && !h_learning_rates))
+        return fail(ICPB_EINVAL, "icpb_pose_graph_sgd: bad argument%s");
+    if (!(loop_closure_uncertainty > 0.0)) return fail(ICPB_EINVAL, "icpb_pose_graph_sgd: loop_closure_uncertainty must be > 0%s");
+    for (int64_t e = 0; e < 2 * n_edges; ++e)
+        if (h_edges[e] < 0 || h_edges[e] >= n) return fail(ICPB_EINVAL, "icpb_pose_graph_sgd: edge endpoint out of range%s");
+    // Edges the optimiser ignores (|a - b| == 1, :14-16 and :28-30) or that have an empty node range
+    // (b <= a: `range(a+1, b+1)` :20 and `i <= b` :46 never hold) move nothing: they stay on the host.
+    std::vector<int32_t> ve;
+    std::vector<double> vt;
+    for (int64_t e = 0; e < n_edges; ++e) {
+        const int32_t ea = h_edges[2 * e], eb = h_edges[2 * e + 1];
+        if (eb > ea + 1) {
+            ve.push_back(ea); ve.push_back(eb);
+            vt.insert(vt.end(), h_edge_T6 + 6 * e, h_edge_T6 + 6 * e + 6);
+        }
+    }
+    if (ve.empty() || n_steps == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const size_t E = ve.size() / 2, N = (size_t)n;
+    // [poses 3N | tf 6E | dW 4E | PB 6E | M 3N | P 3N] doubles, then [edges 2E] int32
+    const size_t n_dbl = 3 * N + 6 * E + 4 * E + 6 * E + 3 * N + 3 * N;
+    int rc;
+    if ((rc = h->s_sgd.reserve(sizeof(double) * n_dbl + sizeof(int32_t) * 2 * E))) return rc;
+    double *d_poses = (double *)h->s_sgd.p, *d_tf = d_poses + 3 * N, *d_dW = d_tf + 6 * E, *d_PB = d_dW + 4 * E;
+    double *d_M = d_PB + 6 * E, *d_P = d_M + 3 * N;
+    int32_t *d_edges = (int32_t *)(d_P + 3 * N);
+    CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_tf, vt.data(), sizeof(double) * 6 * E, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_edges, ve.data(), sizeof(int32_t) * 2 * E, cudaMemcpyHostToDevice, h->stream));
+    icpb::SgdArgs a;
+    a.poses = d_poses; a.edges = d_edges; a.tf = d_tf; a.n = (int32_t)n; a.E = (int32_t)E;
+    a.lcu = loop_closure_uncertainty; a.dW = d_dW; a.PB = d_PB; a.M = d_M; a.P = d_P;
+    // poses in shared memory: one CTA up to 9,600 nodes, a thread-block cluster of up to 8 CTAs
+    // (one slice of nodes each, distributed shared memory) up to 76,800, global memory beyond that
+    const size_t smem_cap = (size_t)kMaxSmem - 1024;                              // ~0.7 KB of static shared memory
+    const size_t node_cap = smem_cap / (3 * sizeof(double));
+    const size_t scan_bytes = sizeof(double) * 3 * icpb::kSgdThreads;
+    int csize = (int)((N + node_cap - 1) / node_cap);
+    if (const char *t = getenv("ICPB_SGD_CLUSTER")) {        // tests: force a cluster size
+        const int v = atoi(t);
+        if (v >= 1 && v <= 8 && (size_t)v * node_cap >= N) csize = v;
+    }
+    a.poses_in_smem = csize <= 8 ? 1 : 0;
+    if (!a.poses_in_smem) csize = 1;
+    a.slice = (int32_t)((N + csize - 1) / csize);
+    size_t dyn = a.poses_in_smem ? sizeof(double) * 3 * (size_t)a.slice : 0;
+    if (dyn < scan_bytes) dyn = scan_bytes;
+    void (*chain)(const icpb::SgdArgs) = csize > 1 ? icpb::sgd_chain_kernel<true> : icpb::sgd_chain_kernel<false>;
+    CU(cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    for (int32_t k = 0; k < n_steps; ++k) {
+        a.learning_rate = h_learning_rates[k];
+        icpb::sgd_weights_kernel<<<(unsigned)((E + 255) / 256), 256, 0, h->stream>>>(a);
+        icpb::sgd_accumulate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(a);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)csize); lc.blockDim = dim3(icpb::kSgdThreads);
+        lc.dynamicSmemBytes = dyn; lc.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr; lc.numAttrs = csize > 1 ? 1 : 0;
+        CU(cudaLaunchKernelEx(&lc, chain, a));
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(h_poses, d_poses, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -166,6 +166,23 @@ int icpb_proximity_pairs(icpb_handle h, const double *h_xy, const double *h_trav
  * Pure host function (no handle): a serial dependency chain. */
 int icpb_compose_chain(const double *pose0, const double *T6, int64_t n, double *poses_out);
 
+/*
+ * Pose-graph relaxation, the consumer of the path's constraints: n_steps
+ * passes of the reference's pose_graph_optimization_step_sgd(pose_graph, learning_rate,
+ * loop_closure_uncertainty) (src/pose_graph_optimization.py:7-49), pass k with
+ * h_learning_rates[k] (scripts/main.py:325-326 uses 1/(k+1)).
+ *   h_poses    n x 3 float64 (x, y, theta) = pose_graph.poses, updated in place
+ *   h_edges    n_edges x 2 int32 (a, b) in the order `pose_graph.graph.edges(data="object")`
+ *              yields them (the optimiser is order dependent); edges with |a - b| == 1 are ignored
+ *              exactly as the reference ignores them (:14-16), edges with b <= a move nothing
+ *   h_edge_T6  n_edges x 6 float64: the top two rows of every edge's 3x3 transform (bottom row
+ *              [0 0 1], as add_constraint receives it from the ICP path, src/pose_graph.py:38-40)
+ * Results agree with the reference to rounding (closed-form 3x3 inverses, prefix sums).
+ */
+int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t *h_edges,
+                        const double *h_edge_T6, int64_t n_edges, const double *h_learning_rates,
+                        int32_t n_steps, double loop_closure_uncertainty);
+
 /* Launch geometry and resource use of the alignment kernel for the current scan table
  * (reported by bench.py next to the roofline numbers). */
 typedef struct icpb_kernel_info {

@@ -31,13 +31,15 @@ def graph_order(loops):
     return sorted(loops, key=lambda e: e[0])
 
 
-def sgd_step(poses, loops, learning_rate=1.0, loop_closure_uncertainty=0.1):
-    """One pass of the reference's modified SGD over the loop edges; mutates and returns poses."""
+def sgd_step(poses, loops, learning_rate=1.0, loop_closure_uncertainty=0.1, in_graph_order=False):
+    """One pass of the reference's modified SGD over the loop edges; mutates and returns poses.
+    `in_graph_order`: `loops` is already in the order the graph iterates its edges (a flipped
+    graph, src/pose_graph.py:42-52, does not iterate by ascending source node)."""
     n = len(poses)
     sigma = np.eye(3) * loop_closure_uncertainty
     weight = np.zeros((n, 3))
     gamma = np.full(3, np.inf)
-    edges = [e for e in graph_order(loops) if abs(e[0] - e[1]) != 1]
+    edges = [e for e in (loops if in_graph_order else graph_order(loops)) if abs(e[0] - e[1]) != 1]
     for a, b, _ in edges:                                        # :13-24
         rot = _rot3(poses[a][2])
         dw = np.diag(np.linalg.inv(rot @ sigma @ rot.T))
