@@ -711,7 +711,10 @@ icp_align_kernel(const KernelArgs a)
         }
         if (a.n_peers > 0 && crank == 0 && tid < 8 * a.n_peers) {
             const int r = tid >> 3, k = tid & 7;                // 8 lanes per peer: one 64-byte record each
-            const double v = k < 6 ? Tw[k] : (k == 6 ? err : (double)passes);
+            // every warp reads its OWN copy of T (identical bits, ordered by its own __syncwarp):
+            // with more than four peers the lanes of warp 1 store too, and warp 0's copy is not
+            // ordered against them
+            const double v = k < 6 ? Tmine[k] : (k == 6 ? err : (double)passes);
             a.peers[r][(a.rec_row0 + pid) * 8 + k] = v;
         }
         if (a.corr) {

@@ -21,8 +21,8 @@ class OracleParams(ctypes.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "icp_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("icp_oracle.c", "grid_oracle.c", "Makefile"))
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libicp_oracle.so"])
     return _SO
 
@@ -106,3 +106,57 @@ def icp_batch(xy, offsets, pairs, init=None, epsilon=0.01, max_iters=100, stoppi
 
 def max_threads() -> int:
     return lib().icp_oracle_max_threads()
+
+
+# ---- occupancy grid (oracle/grid_oracle.c; reference src/produce_occupancy_grid.py) ----------------
+
+def global_points(poses, xy, offsets):
+    """construct_global_points (:84-94) over a CSR scan table; returns (sum m_i, 2)."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64)
+    out = np.empty_like(xy)
+    lib().grid_oracle_global_points(_p(poses, ctypes.c_double), _p(xy, ctypes.c_double),
+                                    _p(offsets, ctypes.c_int64), ctypes.c_int64(len(poses)),
+                                    _p(out, ctypes.c_double))
+    return out
+
+
+def grid_bounds(gxy, cell_width, min_width=0, min_height=0):
+    """produce_occupancy_grid :29-51: (min_x, min_y, height_in_cells, width_in_cells)."""
+    min_x = np.min(gxy[:, 0]) - (cell_width / 2)
+    max_x = np.max(gxy[:, 0]) + (cell_width / 2)
+    min_y = np.min(gxy[:, 1]) - (cell_width / 2)
+    max_y = np.max(gxy[:, 1]) + (cell_width / 2)
+    width_dist = max_x - min_x
+    height_dist = max_y - min_y
+    if width_dist < min_width:
+        offset = (min_width - width_dist) / 2
+        min_x -= offset
+        width_dist = min_width
+    if height_dist < min_height:
+        offset = (min_height - height_dist) / 2
+        min_y -= offset
+        height_dist = min_height
+    return (float(min_x), float(min_y), int(np.ceil(height_dist / cell_width)),
+            int(np.ceil(width_dist / cell_width)))
+
+
+def update_grid(grid, poses, xy, offsets, cell_width, min_x, min_y, k_hit=3, k_miss=1):
+    """update_occupancy_grid (:60-80), in place on an int8 (h, w) C-contiguous grid."""
+    assert grid.dtype == np.int8 and grid.flags.c_contiguous
+    poses = np.ascontiguousarray(poses, dtype=np.float64)
+    gxy = global_points(poses, xy, offsets)
+    lib().grid_oracle_update(grid.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+                             ctypes.c_int64(grid.shape[0]), ctypes.c_int64(grid.shape[1]),
+                             _p(poses, ctypes.c_double), _p(gxy, ctypes.c_double), _p(offsets, ctypes.c_int64),
+                             ctypes.c_int64(len(poses)), ctypes.c_double(min_x), ctypes.c_double(min_y),
+                             ctypes.c_double(cell_width), ctypes.c_int(k_hit), ctypes.c_int(k_miss))
+    return grid
+
+
+def produce_grid(poses, xy, offsets, cell_width, min_width=0, min_height=0, k_hit=3, k_miss=1):
+    """produce_occupancy_grid (:11-58): returns (grid int8 (h, w), (min_x, min_y))."""
+    gxy = global_points(poses, xy, offsets)
+    min_x, min_y, h, w = grid_bounds(gxy, cell_width, min_width, min_height)
+    grid = np.zeros((h, w), dtype=np.int8)
+    update_grid(grid, poses, xy, offsets, cell_width, min_x, min_y, k_hit, k_miss)
+    return grid, (min_x, min_y)

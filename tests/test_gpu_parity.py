@@ -471,3 +471,34 @@ def test_fused_gather_epilogue_single_rank(gicp):
     np.testing.assert_array_equal(got[row0:row0 + B, 7], ref.iters)
     assert np.all(got[:row0] == -1) and np.all(got[row0 + B:] == -1)
     e.close()
+
+
+@pytest.mark.parametrize("n_peers", [2, 5, 8])
+def test_fused_gather_epilogue_many_peers(gicp, n_peers):
+    """Up to 8 peer buffers (here all on this GPU): with more than four peers the stores are issued
+    by two warps of the CTA, and every buffer must still receive the final transform of every pair
+    (a 1,024-beam, 600-pair batch so that many CTAs finish pairs concurrently)."""
+    import torch
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(601, 1024, seed=92)
+    e = gicp.IcpEngine()
+    e.set_scans(scans)
+    ref = e.run(pairs, init, epsilon=0.05)
+    dev = torch.device("cuda", e.device)
+    B = len(pairs)
+    bufs = [torch.full((B, 8), -1.0, dtype=torch.float64, device=dev) for _ in range(n_peers)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    pairs_t = torch.from_numpy(pairs).to(dev)
+    init_t = torch.from_numpy(np.ascontiguousarray(init[:, :2, :].reshape(B, 6))).to(dev)
+    oT = torch.empty((B, 6), dtype=torch.float64, device=dev)
+    oe = torch.empty(B, dtype=torch.float64, device=dev)
+    op = torch.empty(B, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        e.run_device_gather(pairs_t, init_t, oT, oe, op, ptrs.data_ptr(), n_peers, 0, epsilon=0.05)
+    torch.cuda.synchronize()
+    for b in bufs:
+        got = b.cpu().numpy()
+        np.testing.assert_array_equal(got[:, :6].reshape(B, 2, 3), ref.T[:, :2, :])
+        np.testing.assert_array_equal(got[:, 6], ref.error)
+        np.testing.assert_array_equal(got[:, 7], ref.iters)
+    e.close()

@@ -105,7 +105,9 @@ def main():
         # every rank holds every rank's records; this rank's block must equal what it computed
         blk = gathered[rank * cap:rank * cap + b_local]
         assert torch.equal(blk[:, :6], out_T) and torch.equal(blk[:, 6], out_err)
-        assert bool((gathered.view(world, cap, 8)[:, :min(cap, b_local), 7] >= 1).all())
+        for r in range(world):                              # no rank's records are missing
+            cnt = len(gdist.shard_indices(B, r, world, args.block))
+            assert bool((gathered[r * cap:r * cap + cnt, 7] >= 1).all()), f"records of rank {r} missing"
 
     # the oracle on a seeded sample of this rank's pairs
     checked, max_dT = 0, 0.0
