@@ -20,7 +20,8 @@ EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destr
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
            "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host",
            "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
-           "icpb_run_device_gather", "icpb_pose_graph_sgd"]
+           "icpb_run_device_gather", "icpb_pose_graph_sgd", "icpb_occupancy_grid_bounds",
+           "icpb_occupancy_grid_update"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -49,6 +50,7 @@ def sources():
     return [os.path.join(c, "icpb_api.cu")], [os.path.join(c, "icpb_kernels.cuh"),
                                               os.path.join(c, "icpb_candidates.cuh"),
                                               os.path.join(c, "icpb_sgd.cuh"),
+                                              os.path.join(c, "icpb_grid.cuh"),
                                               os.path.join(_ROOT, "include", "icpb.h")]
 
 
@@ -95,6 +97,11 @@ def lib() -> ctypes.CDLL:
                                        ctypes.POINTER(ctypes.c_int64)]
     L.icpb_compose_chain.argtypes = [dp, dp, i64, dp]
     L.icpb_pose_graph_sgd.argtypes = [vp, dp, i64, i32p, dp, i64, dp, ctypes.c_int32, ctypes.c_double]
+    L.icpb_occupancy_grid_bounds.argtypes = [vp, dp, i64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    L.icpb_occupancy_grid_update.argtypes = [vp, dp, i64, vp, i64, i64, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_int32, ctypes.c_int32]
     L.icpb_fit_pairs_host.argtypes = [vp, dp, dp, i64, dp, dp]
     L.icpb_icp_pair_host.argtypes = [vp, dp, i64, dp, i64, dp, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_get_kernel_info.argtypes = [vp, i64, ctypes.POINTER(IcpbKernelInfo)]

@@ -13,6 +13,7 @@
 #include "icpb_kernels.cuh"
 #include "icpb_candidates.cuh"
 #include "icpb_sgd.cuh"
+#include "icpb_grid.cuh"
 
 namespace {
 
@@ -118,6 +119,7 @@ struct icpb_ctx {
     DevBuf s_seg;
     PinnedBuf stage;                                // pinned staging of the small per-call arrays
     DevBuf s_sgd;                                   // pose-graph SGD: poses, edges, transforms, scratch
+    DevBuf s_grid;                                  // occupancy grid: poses, per-cell words, the grid
     int max_smem_set = 0;
 };
 
@@ -301,7 +303,7 @@ int icpb_destroy(icpb_handle h)
     for (int k = 0; k < 2; ++k) if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
     if (h->arrived_dev) cudaFree(h->arrived_dev);
     if (h->seg_vals_pinned) cudaFreeHost(h->seg_vals_pinned);
-    h->s_seg.release(); h->stage.release(); h->s_sgd.release();
+    h->s_seg.release(); h->stage.release(); h->s_sgd.release(); h->s_grid.release();
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -793,6 +795,100 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(h_poses, d_poses, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* ---- occupancy grid (include/icpb.h; reference src/produce_occupancy_grid.py) ---- */
+namespace {
+
+int grid_check(icpb_handle h, const double *h_poses, int64_t n, double cell_width, const char *who)
+{
+    if (!h || !h_poses || n <= 0 || !(cell_width > 0.0)) return fail(ICPB_EINVAL, "%s: bad argument", who);
+    if (!h->xy) return fail(ICPB_ENOSCANS, "%s: no scan table set", who);
+    if (n > h->n_scans) return fail(ICPB_EINVAL, "%s: more poses than scans in the table", who);
+    return 0;
+}
+
+double key_to_double(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    double v;
+    memcpy(&v, &b, sizeof v);
+    return v;
+}
+
+}  // namespace
+
+int icpb_occupancy_grid_bounds(icpb_handle h, const double *h_poses, int64_t n, double cell_width,
+                               double min_width, double min_height, double *min_x_out, double *min_y_out,
+                               int64_t *height, int64_t *width)
+{
+    int rc = grid_check(h, h_poses, n, cell_width, "icpb_occupancy_grid_bounds");
+    if (rc) return rc;
+    if (!min_x_out || !min_y_out || !height || !width) return fail(ICPB_EINVAL, "icpb_occupancy_grid_bounds: null output%s");
+    CU(cudaSetDevice(h->device));
+    if ((rc = h->s_grid.reserve(sizeof(double) * 3 * (size_t)n + 4 * sizeof(unsigned long long)))) return rc;
+    unsigned long long *d_mm = (unsigned long long *)h->s_grid.p;
+    double *d_poses = (double *)(d_mm + 4);
+    const unsigned long long init[4] = {~0ULL, ~0ULL, 0ULL, 0ULL};
+    CU(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    icpb::GridArgs a = {};
+    a.xy = h->xy; a.offsets = h->offsets; a.poses = d_poses; a.n = (int32_t)n;
+    icpb::grid_bounds_kernel<<<(unsigned)n, 256, 0, h->stream>>>(a, d_mm);
+    CU(cudaGetLastError());
+    unsigned long long mm[4];
+    CU(cudaMemcpyAsync(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (mm[0] == ~0ULL) return fail(ICPB_EINVAL, "icpb_occupancy_grid_bounds: the scans hold no points%s");
+    // src/produce_occupancy_grid.py:30-51, operation for operation
+    double min_x = key_to_double(mm[0]) - (cell_width / 2), max_x = key_to_double(mm[2]) + (cell_width / 2);
+    double min_y = key_to_double(mm[1]) - (cell_width / 2), max_y = key_to_double(mm[3]) + (cell_width / 2);
+    double width_dist = max_x - min_x, height_dist = max_y - min_y;
+    if (width_dist < min_width) { const double off = (min_width - width_dist) / 2; min_x -= off; width_dist = min_width; }
+    if (height_dist < min_height) { const double off = (min_height - height_dist) / 2; min_y -= off; height_dist = min_height; }
+    *min_x_out = min_x; *min_y_out = min_y;
+    *width = (int64_t)ceil(width_dist / cell_width);
+    *height = (int64_t)ceil(height_dist / cell_width);
+    return 0;
+}
+
+int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, int8_t *h_grid,
+                               int64_t height, int64_t width, double min_x, double min_y,
+                               double cell_width, int32_t k_hit, int32_t k_miss)
+{
+    int rc = grid_check(h, h_poses, n, cell_width, "icpb_occupancy_grid_update");
+    if (rc) return rc;
+    if (!h_grid || height <= 0 || width <= 0 || height > 0x7fffffff || width > 0x7fffffff ||
+        height * width > ((int64_t)1 << 34))
+        return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: bad grid%s");
+    // the per-cell closed form needs a miss to leave a cell negative and a hit to leave it positive
+    if (k_hit < 1 || k_hit > 127 || k_miss < 1 || k_miss > 127)
+        return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: kHitOdds and kMissOdds must be integers in 1..127%s");
+    CU(cudaSetDevice(h->device));
+    // the beam order keys are 32 bit: 2 * (beam index + 1) + 1 must fit (2^31 - 2 beams)
+    int64_t n_points = 0;
+    CU(cudaMemcpy(&n_points, h->offsets + n, sizeof n_points, cudaMemcpyDeviceToHost));
+    if (n_points >= 0x7ffffffeLL) return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: more than 2^31 - 2 beams in one call%s");
+    const size_t cells = (size_t)height * (size_t)width;
+    const size_t words = 3 * cells;
+    if ((rc = h->s_grid.reserve(sizeof(double) * 3 * (size_t)n + sizeof(uint32_t) * words + cells + 64))) return rc;
+    double *d_poses = (double *)h->s_grid.p;
+    uint32_t *d_words = (uint32_t *)(d_poses + 3 * (size_t)n);
+    int8_t *d_grid = (int8_t *)(d_words + words);
+    CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_grid, h_grid, cells, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(d_words, 0, sizeof(uint32_t) * words, h->stream));
+    icpb::GridArgs a = {};
+    a.xy = h->xy; a.offsets = h->offsets; a.poses = d_poses; a.n = (int32_t)n;
+    a.min_x = min_x; a.min_y = min_y; a.cell = cell_width; a.h = (int32_t)height; a.w = (int32_t)width;
+    a.last = d_words; a.n_miss = d_words + cells; a.n_hit = d_words + 2 * cells;
+    icpb::grid_beams_kernel<<<(unsigned)n, 256, 0, h->stream>>>(a);
+    CU(cudaGetLastError());
+    icpb::grid_finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(a, d_grid, k_hit, k_miss);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_grid, d_grid, cells, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -183,6 +183,27 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
                         const double *h_edge_T6, int64_t n_edges, const double *h_learning_rates,
                         int32_t n_steps, double loop_closure_uncertainty);
 
+/*
+ * Occupancy grid from the optimised poses and the scans:
+ * produce_occupancy_grid(poses, lidar_points, cell_width, min_width, min_height, kHitOdds, kMissOdds)
+ * and update_occupancy_grid(...) (src/produce_occupancy_grid.py:11-80).  Pose i belongs to scan i
+ * of the handle's scan table (icpb_upload_scans); n <= number of scans.
+ *
+ * icpb_occupancy_grid_bounds: the grid origin and size of :27-51 (bounding box of all beam end
+ *   points in the global frame, half a cell of margin, optional minimum size).
+ * icpb_occupancy_grid_update: the double loop over beams of :54-56 / :76-78 -- a Bresenham walk per
+ *   beam (:96-131), "miss" on every crossed cell, "hit" on the last -- applied to h_grid
+ *   (height x width int8, row 0 at min_y, C order), in place.  Bit-identical to the reference's
+ *   sequential loops, including its int8 wrap-around at :109 and :128 (see csrc/icpb_grid.cuh).
+ *   kHitOdds and kMissOdds must be integers in 1..127.
+ */
+int icpb_occupancy_grid_bounds(icpb_handle h, const double *h_poses, int64_t n, double cell_width,
+                               double min_width, double min_height, double *min_x, double *min_y,
+                               int64_t *height, int64_t *width);
+int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, int8_t *h_grid,
+                               int64_t height, int64_t width, double min_x, double min_y,
+                               double cell_width, int32_t k_hit, int32_t k_miss);
+
 /* Launch geometry and resource use of the alignment kernel for the current scan table
  * (reported by bench.py next to the roofline numbers). */
 typedef struct icpb_kernel_info {
