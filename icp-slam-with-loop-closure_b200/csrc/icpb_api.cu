@@ -810,6 +810,17 @@ int grid_check(icpb_handle h, const double *h_poses, int64_t n, double cell_widt
     return 0;
 }
 
+// (cos theta, sin theta, x, y) per pose: odom_change_to_mat's trigonometry (src/utils.py:8-9) in libm
+std::vector<double> pose_records(const double *h_poses, int64_t n)
+{
+    std::vector<double> r(4 * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        r[4 * i] = cos(h_poses[3 * i + 2]); r[4 * i + 1] = sin(h_poses[3 * i + 2]);
+        r[4 * i + 2] = h_poses[3 * i]; r[4 * i + 3] = h_poses[3 * i + 1];
+    }
+    return r;
+}
+
 double key_to_double(unsigned long long k)
 {
     const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
@@ -828,12 +839,13 @@ int icpb_occupancy_grid_bounds(icpb_handle h, const double *h_poses, int64_t n, 
     if (rc) return rc;
     if (!min_x_out || !min_y_out || !height || !width) return fail(ICPB_EINVAL, "icpb_occupancy_grid_bounds: null output%s");
     CU(cudaSetDevice(h->device));
-    if ((rc = h->s_grid.reserve(sizeof(double) * 3 * (size_t)n + 4 * sizeof(unsigned long long)))) return rc;
+    if ((rc = h->s_grid.reserve(sizeof(double) * 4 * (size_t)n + 4 * sizeof(unsigned long long)))) return rc;
     unsigned long long *d_mm = (unsigned long long *)h->s_grid.p;
     double *d_poses = (double *)(d_mm + 4);
     const unsigned long long init[4] = {~0ULL, ~0ULL, 0ULL, 0ULL};
+    const std::vector<double> rec = pose_records(h_poses, n);
     CU(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_poses, rec.data(), sizeof(double) * 4 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     icpb::GridArgs a = {};
     a.xy = h->xy; a.offsets = h->offsets; a.poses = d_poses; a.n = (int32_t)n;
     icpb::grid_bounds_kernel<<<(unsigned)n, 256, 0, h->stream>>>(a, d_mm);
@@ -873,11 +885,12 @@ int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, 
     if (n_points >= 0x7ffffffeLL) return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: more than 2^31 - 2 beams in one call%s");
     const size_t cells = (size_t)height * (size_t)width;
     const size_t words = 3 * cells;
-    if ((rc = h->s_grid.reserve(sizeof(double) * 3 * (size_t)n + sizeof(uint32_t) * words + cells + 64))) return rc;
+    if ((rc = h->s_grid.reserve(sizeof(double) * 4 * (size_t)n + sizeof(uint32_t) * words + cells + 64))) return rc;
     double *d_poses = (double *)h->s_grid.p;
-    uint32_t *d_words = (uint32_t *)(d_poses + 3 * (size_t)n);
+    uint32_t *d_words = (uint32_t *)(d_poses + 4 * (size_t)n);
     int8_t *d_grid = (int8_t *)(d_words + words);
-    CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    const std::vector<double> rec = pose_records(h_poses, n);
+    CU(cudaMemcpyAsync(d_poses, rec.data(), sizeof(double) * 4 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_grid, h_grid, cells, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(d_words, 0, sizeof(uint32_t) * words, h->stream));
     icpb::GridArgs a = {};

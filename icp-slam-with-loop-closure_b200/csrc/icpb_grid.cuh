@@ -26,7 +26,9 @@ namespace icpb {
 struct GridArgs {
     const double  *xy;        // scan table (sum m_i, 2), points in each scan's local frame
     const int64_t *offsets;   // CSR offsets
-    const double  *poses;     // n x 3 (x, y, theta)
+    const double  *poses;     // n x 4 (cos theta, sin theta, x, y): the trigonometry is done on the host
+                              // with libm, whose bits numpy's cos/sin match (src/utils.py:8-9); CUDA's
+                              // sincos can differ in the last place, which would move cell boundaries
     int32_t        n;         // scans / poses
     double         min_x, min_y, cell;
     int32_t        h, w;      // grid size in cells
@@ -57,9 +59,7 @@ __global__ void __launch_bounds__(256)
 grid_bounds_kernel(const GridArgs a, unsigned long long *mm)
 {
     const int i = blockIdx.x;
-    double s, c;
-    sincos(a.poses[3 * i + 2], &s, &c);
-    const double px = a.poses[3 * i], py = a.poses[3 * i + 1];
+    const double c = a.poses[4 * i], s = a.poses[4 * i + 1], px = a.poses[4 * i + 2], py = a.poses[4 * i + 3];
     unsigned long long lox = ~0ULL, loy = ~0ULL, hix = 0ULL, hiy = 0ULL;
     for (int64_t k = a.offsets[i] + threadIdx.x; k < a.offsets[i + 1]; k += blockDim.x) {
         double gx, gy;
@@ -91,9 +91,7 @@ grid_beams_kernel(const GridArgs a)
 {
     const int i = blockIdx.x;                                   // scan
     const int lane = threadIdx.x & 31;
-    double s, c;
-    sincos(a.poses[3 * i + 2], &s, &c);
-    const double px = a.poses[3 * i], py = a.poses[3 * i + 1];
+    const double c = a.poses[4 * i], s = a.poses[4 * i + 1], px = a.poses[4 * i + 2], py = a.poses[4 * i + 3];
     const int64_t k_begin = a.offsets[i], k_end = a.offsets[i + 1];
     const long long W = a.w, H = a.h;
     for (int64_t kw = k_begin + (threadIdx.x & ~31); kw < k_end; kw += blockDim.x) {

@@ -31,8 +31,9 @@ def _stage(poses, lidar_points, device):
     poses = np.ascontiguousarray(poses, dtype=np.float64)
     if poses.ndim != 2 or poses.shape[1] != 3:
         raise ValueError(f"poses has shape {poses.shape}; expected (n, 3)")
-    if len(lidar_points) != len(poses):
-        raise ValueError(f"{len(poses)} poses for {len(lidar_points)} scans")
+    n_scans = lidar_points.n_scans if isinstance(lidar_points, _icp.ScanTable) else len(lidar_points)
+    if n_scans != len(poses):
+        raise ValueError(f"{len(poses)} poses for {n_scans} scans")
     eng = _icp.engine(device)
     if isinstance(lidar_points, _icp.ScanTable):
         if eng.table is not lidar_points:

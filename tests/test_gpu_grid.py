@@ -54,7 +54,7 @@ def test_larger_maps_against_the_sequential_oracle(n_scans, beams, cell, odds):
     got, origin_g = pog.produce_occupancy_grid(poses, scans, cell, kHitOdds=odds[0], kMissOdds=odds[1])
     assert origin_g == origin_w and got.shape == want.shape
     np.testing.assert_array_equal(got, want)
-    assert (want > 0).sum() > 50 and (want < 0).sum() > 1000
+    assert (want > 0).sum() > 50 and (want < 0).sum() > 500
     # a second sweep over the same map from other poses: update in place
     poses2 = poses[::3] + np.array([0.3, -0.2, 0.1])
     scans2 = scans[::3]
