@@ -873,7 +873,7 @@ int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, 
     int rc = grid_check(h, h_poses, n, cell_width, "icpb_occupancy_grid_update");
     if (rc) return rc;
     if (!h_grid || height <= 0 || width <= 0 || height > 0x7fffffff || width > 0x7fffffff ||
-        height * width > ((int64_t)1 << 34))
+        height * width > ((int64_t)1 << 30))
         return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: bad grid%s");
     // the per-cell closed form needs a miss to leave a cell negative and a hit to leave it positive
     if (k_hit < 1 || k_hit > 127 || k_miss < 1 || k_miss > 127)
@@ -884,7 +884,7 @@ int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, 
     CU(cudaMemcpy(&n_points, h->offsets + n, sizeof n_points, cudaMemcpyDeviceToHost));
     if (n_points >= 0x7ffffffeLL) return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: more than 2^31 - 2 beams in one call%s");
     const size_t cells = (size_t)height * (size_t)width;
-    const size_t words = 3 * cells;
+    const size_t words = 4 * cells;
     if ((rc = h->s_grid.reserve(sizeof(double) * 4 * (size_t)n + sizeof(uint32_t) * words + cells + 64))) return rc;
     double *d_poses = (double *)h->s_grid.p;
     uint32_t *d_words = (uint32_t *)(d_poses + 4 * (size_t)n);
@@ -896,8 +896,10 @@ int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, 
     icpb::GridArgs a = {};
     a.xy = h->xy; a.offsets = h->offsets; a.poses = d_poses; a.n = (int32_t)n;
     a.min_x = min_x; a.min_y = min_y; a.cell = cell_width; a.h = (int32_t)height; a.w = (int32_t)width;
-    a.last = d_words; a.n_miss = d_words + cells; a.n_hit = d_words + 2 * cells;
-    icpb::grid_beams_kernel<<<(unsigned)n, 256, 0, h->stream>>>(a);
+    a.last_hit = d_words; a.n_miss = d_words + cells; a.n_hit = d_words + 2 * cells; a.miss_after = d_words + 3 * cells;
+    icpb::grid_hits_kernel<<<(unsigned)n, 256, 0, h->stream>>>(a);
+    CU(cudaGetLastError());
+    icpb::grid_misses_kernel<<<(unsigned)n, 256, 0, h->stream>>>(a);
     CU(cudaGetLastError());
     icpb::grid_finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(a, d_grid, k_hit, k_miss);
     CU(cudaGetLastError());
