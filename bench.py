@@ -150,6 +150,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_ALL_CPUS = None
+
+
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this rank's host threads on the CPUs next to its GPU, so the pinned
+    staging buffers (first touch) and the copy-engine reads stay on the local memory controller and
+    PCIe root -- with 8 ranks uploading at once the cross-socket link is otherwise shared by all of
+    them.  Returns a short description for the JSON line; never fatal."""
+    global _ALL_CPUS
+    try:
+        _ALL_CPUS = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus ({cpus[0]}-{cpus[-1]})"
+    except Exception as exc:                                  # noqa: BLE001
+        return f"unbound ({type(exc).__name__})"
+
+
 def cpu_port_rate(scans, pairs, init, seconds, threads=0):
     """Time the C port of the reference algorithm on a bounded sample of the same workload."""
     from oracle import c_oracle
@@ -225,6 +246,7 @@ def main():
     import torch.distributed as dist
     from icp_slam_b200 import icp as gicp
 
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # NCCL prints its version banner on stdout at communicator creation; keep stdout for the one
@@ -430,6 +452,8 @@ def main():
         }
         cpu = None
         if world == 1 and not args.no_cpu:
+            if _ALL_CPUS:
+                os.sched_setaffinity(0, _ALL_CPUS)            # the CPU baseline gets every host core back
             rate, nthr, n, dt, mean_pass = cpu_port_rate(scans, pairs, init, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
                    "sample": f"{n} of {B} chain pairs (seeded random subsample) in {dt:.1f} s, "
@@ -446,7 +470,7 @@ def main():
                                       "fused: kernel epilogue stores (B,8) f64 records into every rank's buffer over "
                                       "NVLink peer memory + symmetric-memory barrier" if symm is not None else
                                       "NCCL all_gather of (B,8) f64 constraint records"),
-                       "kernel": info},
+                       "kernel": info, "host_affinity": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -27,6 +27,19 @@ def chain_pairs(n_scans: int, stride: int = 1, start: int = 0) -> np.ndarray:
     return np.stack((idx, idx - stride), axis=1).astype(np.int32)
 
 
+def poses_to_mats(poses) -> np.ndarray:
+    """``utils.pose_to_mat`` (src/utils.py:28-33) for an (n, 3) array of poses at once: (n, 3, 3).
+    numpy's cos/sin give the same bits on arrays as on scalars, so this equals the reference's
+    per-pose calls."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 3)
+    c, s = np.cos(poses[:, 2]), np.sin(poses[:, 2])
+    out = np.zeros((len(poses), 3, 3))
+    out[:, 0, 0] = c; out[:, 0, 1] = -s; out[:, 0, 2] = poses[:, 0]
+    out[:, 1, 0] = s; out[:, 1, 1] = c; out[:, 1, 2] = poses[:, 1]
+    out[:, 2, 2] = 1.0
+    return out
+
+
 def odometry_chain(lidar_points, odometry, max_iters=100, epsilon=0.05, device=None):
     """ICP-corrected poses of the whole trajectory (scripts/main.py:239-256).
 
@@ -36,7 +49,7 @@ def odometry_chain(lidar_points, odometry, max_iters=100, epsilon=0.05, device=N
     odometry = np.asarray(odometry, dtype=np.float64)
     n = len(odometry)
     pairs = chain_pairs(n)
-    init = np.stack([pose_to_mat(odometry[i] - odometry[i - 1]) for i in range(1, n)])
+    init = poses_to_mats(odometry[1:] - odometry[:-1])
     res = _icp.icp_batch(lidar_points, pairs, init, epsilon=epsilon, max_iters=max_iters, device=device)
     return compose_chain(odometry[0], res.T), res
 
@@ -152,10 +165,10 @@ def rotation_only_headings(poses, lidar_points, max_iters=100, epsilon=0.05, dev
     poses = np.array(poses, dtype=np.float64)
     n = len(poses)
     pairs = chain_pairs(n)
-    init = np.stack([pose_to_mat(poses[i] - poses[i - 1]) for i in range(1, n)])
+    init = poses_to_mats(poses[1:] - poses[:-1])
     res = _icp.icp_batch(lidar_points, pairs, init, epsilon=epsilon, max_iters=max_iters,
                          rotation_only=True, device=device)
-    for i in range(n - 1, 0, -1):                            # the reference sweeps from the end (:70-74)
-        T = res.T[i - 1]
-        poses[i, 2] = poses[i - 1, 2] + np.arctan2(T[1, 0], T[0, 0])
+    # the reference sweeps from the end (:70-74), so pose i-1 still holds its OLD heading when pose i
+    # is rewritten: one vector expression
+    poses[1:, 2] = poses[:-1, 2].copy() + np.arctan2(res.T[:, 1, 0], res.T[:, 0, 0])
     return poses, res

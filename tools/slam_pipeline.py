@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""The reference's scripts/main.py flow, stage by stage, on the drop-in modules (synthetic data):
+
+  scan matching   odometry ICP chain + composition          scripts/main.py:239-256
+  loop closure    detect_proximity                           src/loop_closure_detection.py:11-39
+  optimisation    SGD passes with learning rate 1/(k+1)      scripts/main.py:322-326
+  orientation     recompute_pose_graph_orientation           src/pose_graph_optimization.py:51-74
+  map             produce_occupancy_grid                     src/produce_occupancy_grid.py:11-58
+
+    python tools/slam_pipeline.py [--scans 5000] [--beams 1024] [--sgd-steps 50] [--cell 0.05]
+
+Prints the wall time of every stage (host to host, after one warm-up of the CUDA context) and the
+absolute trajectory error against the synthetic ground truth before and after optimisation.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+class PoseGraph:
+    """The part of the reference's PoseGraph (src/pose_graph.py:22-40) the pipeline touches, without
+    networkx: edges iterate by source node, then insertion order, like nx.DiGraph.edges."""
+
+    class _Edges:
+        def __init__(self, n):
+            self.adj = [dict() for _ in range(n)]
+
+        def add(self, a, b, tf):
+            self.adj[a][b] = tf
+
+        def edges(self, data=None):
+            return [((a, b, tf) if data else (a, b)) for a, nb in enumerate(self.adj) for b, tf in nb.items()]
+
+    def __init__(self, poses):
+        self.poses = poses
+        self.graph = self._Edges(len(poses))
+        for i in range(len(poses) - 1):
+            self.graph.add(i, i + 1, None)                       # odometry edges: ignored by the optimiser
+
+    def add_constraint(self, i, j, tf):
+        self.graph.add(int(i), int(j), tf)
+
+
+def ate(a, b):
+    d = a[:, :2] - b[:, :2]
+    return float(np.sqrt(np.mean(np.sum(d * d, axis=1))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scans", type=int, default=5000)
+    ap.add_argument("--beams", type=int, default=1024)
+    ap.add_argument("--sgd-steps", type=int, default=50)
+    ap.add_argument("--cell", type=float, default=0.05)
+    args = ap.parse_args()
+    from icp_slam_b200 import (callers, icp as gicp, loop_closure_detection as lcd,
+                               pose_graph_optimization as pgo, produce_occupancy_grid as pog, synth)
+
+    scans, pairs, init, truth, odo = synth.make_chain_workload(args.scans, args.beams, seed=467070)
+    c0, s0 = np.cos(-truth[0, 2]), np.sin(-truth[0, 2])
+    d0 = truth[:, :2] - truth[0, :2]
+    truth0 = np.stack((c0 * d0[:, 0] - s0 * d0[:, 1], s0 * d0[:, 0] + c0 * d0[:, 1], truth[:, 2] - truth[0, 2]), axis=1)
+    odo0 = odo - odo[0]
+    table = gicp.ScanTable(scans)
+    gicp.icp_batch(scans[:4], np.array([[1, 0]], dtype=np.int32))          # CUDA context, first-use costs
+    stages = {}
+
+    def timed(name, fn):
+        t = time.perf_counter()
+        out = fn()
+        stages[name] = (time.perf_counter() - t) * 1e3
+        return out
+
+    corrected, res = timed("scan_matching", lambda: callers.odometry_chain(table, odo0, max_iters=100, epsilon=0.05))
+    pg = PoseGraph(corrected.copy())
+    loops = timed("loop_closure", lambda: lcd.detect_proximity(pg, table))
+    timed("optimisation", lambda: pgo.optimise(pg, args.sgd_steps))
+    optimised = pg.poses.copy()
+    timed("orientation", lambda: pgo.recompute_pose_graph_orientation(pg, table, 100, 0.05, icp_recompute=True))
+    grid, origin = timed("occupancy_grid", lambda: pog.produce_occupancy_grid(pg.poses, table, args.cell))
+    print(json.dumps({
+        "scans": args.scans, "beams_per_scan": args.beams, "chain_pairs": len(pairs),
+        "mean_chain_passes": float(res.iters.mean()), "loop_closures": len(loops), "sgd_steps": args.sgd_steps,
+        "grid": list(grid.shape), "stage_ms": {k: round(v, 2) for k, v in stages.items()},
+        "total_ms": round(sum(stages.values()), 2),
+        "ate_m": {"scan_matching": ate(corrected, truth0), "optimised": ate(optimised, truth0)},
+    }))
+
+
+if __name__ == "__main__":
+    main()
