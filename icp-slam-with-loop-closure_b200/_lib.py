@@ -57,14 +57,24 @@ def sources():
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libicpb.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs, deps = sources()
-    newest = max(os.path.getmtime(p) for p in srcs + deps)
-    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= newest:
+
+    def stale():
+        newest = max(os.path.getmtime(p) for p in srcs + deps)
+        return not os.path.exists(SO_PATH) or os.path.getmtime(SO_PATH) < newest
+    if not force and not stale():
         return SO_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
-                                   "-o", SO_PATH] + srcs
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    subprocess.check_call(cmd)
+    import fcntl
+    # several ranks may get here at once: one builds under the lock into a private name and renames
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if force or stale():
+            tmp = f"{SO_PATH}.{os.getpid()}.tmp"
+            cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
+                                           "-o", tmp] + srcs
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            subprocess.check_call(cmd)
+            os.replace(tmp, SO_PATH)
     return SO_PATH
 
 

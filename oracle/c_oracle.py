@@ -21,9 +21,19 @@ class OracleParams(ctypes.Structure):
 
 
 def build(force: bool = False) -> str:
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("icp_oracle.c", "grid_oracle.c", "Makefile"))
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
-        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libicp_oracle.so"])
+    """Rebuild when a source is newer than the library.  Several processes (ranks, test workers)
+    may get here at once: one builds under a file lock into a private name and renames it into place."""
+    def stale():
+        newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("icp_oracle.c", "grid_oracle.c", "Makefile"))
+        return not os.path.exists(_SO) or os.path.getmtime(_SO) < newest
+    if force or stale():
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if force or stale():
+                tmp = f"libicp_oracle.{os.getpid()}.tmp.so"
+                subprocess.check_call(["make", "-s", "-C", _HERE, "-B", f"OUT={tmp}"])
+                os.replace(os.path.join(_HERE, tmp), _SO)
     return _SO
 
 

@@ -13,6 +13,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 /* numpy's (3,3) @ (3,1) product as this image's OpenBLAS evaluates it, found by matching bits
  * against numpy (tests/golden/make_grid_golden.py): fma(m00, x, m01*y) + m02. */
