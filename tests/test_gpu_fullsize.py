@@ -108,3 +108,20 @@ def test_config5_highres_multistart():
     np.testing.assert_allclose(res.error, err, rtol=1e-9)
     best = int(np.argmin(res.error[:K]))
     assert abs(th[best]) < 1.0                                   # the sweep finds the small-motion basin
+
+
+def test_parity_campaign_reduced():
+    """tools/parity_campaign.py at 4 % of its size (chains, rotation-only, all pairs, ragged clouds
+    incl. tie-laden lattices and far-from-origin coordinates): no pass-count mismatch, no differing
+    correspondence vector, |dT| < 1e-9; a disagreeing pair is excused only when the numpy oracle
+    proves a single-target pass.  The full run (25,172 pairs) is profiles/r01l_parity_campaign.json."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "parity_campaign.py"), "--scale", "0.04",
+                          "--corr-sample", "60"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-2000:])
+    last = json.loads(out.stdout.strip().splitlines()[-1])
+    assert last["all_within_contract"] and last["pairs_total"] > 400
