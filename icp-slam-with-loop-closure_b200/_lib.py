@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
 EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destroy",
            "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
-           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_fit_pairs_host",
+           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_align_host_ld", "icpb_fit_pairs_host",
            "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
            "icpb_run_device_gather", "icpb_pose_graph_sgd", "icpb_occupancy_grid_bounds",
            "icpb_occupancy_grid_update"]
@@ -102,6 +102,8 @@ def lib() -> ctypes.CDLL:
                                          ctypes.c_int32, i64, vp]
     L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_align_host.argtypes = [vp, dp, vp, i64, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p]
+    L.icpb_align_host_ld.argtypes = [vp, dp, vp, i64, i32p, dp, ctypes.c_int32, i64, ctypes.POINTER(IcpbParams),
+                                     dp, ctypes.c_int32, dp, i32p]
     L.icpb_proximity_closest.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i32p, dp]
     L.icpb_proximity_pairs.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i64, i32p,
                                        ctypes.POINTER(ctypes.c_int64)]

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <time.h>
 
 #include "icpb.h"
 #include "icpb_kernels.cuh"
@@ -58,6 +59,14 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// host clock in microseconds (ICPB_TRACE timings of the host entry points)
+static double now_us()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
 struct PinnedBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -74,6 +83,8 @@ struct PinnedBuf {
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
+
+constexpr int kMaxSegments = 64;        // pieces of the streaming scan-table upload (icpb_align_host)
 
 struct LaunchCfg {
     int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ntile_cap, ctas_per_sm;
@@ -115,7 +126,10 @@ struct icpb_ctx {
     cudaEvent_t seg_ev[16] = {};                    // "scan segment k has arrived"
     cudaEvent_t done_ev[2] = {};
     int32_t *arrived_dev = nullptr;                 // streaming upload: segments delivered so far
-    int32_t *seg_vals_pinned = nullptr;             // 1..17 in pinned host memory (sources of the flag copies)
+    // cuStreamWriteValue32 (driver API, looked up at run time): a stream-ordered 4-byte store, cheaper
+    // than a 4-byte DMA for the "segment k has arrived" counter; nullptr -> the counter is copied
+    int (*write32)(cudaStream_t, unsigned long long, unsigned int, unsigned int) = nullptr;
+    int32_t *seg_vals_pinned = nullptr;             // 0..kMaxSegments in pinned host memory (sources of the flag copies)
     DevBuf s_seg;
     PinnedBuf stage;                                // pinned staging of the small per-call arrays
     DevBuf s_sgd;                                   // pose-graph SGD: poses, edges, transforms, scratch
@@ -198,7 +212,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
            cudaStream_t stream, int64_t B_total = 0, const int32_t *d_seg_of_pair = nullptr,
            const int32_t *d_arrived = nullptr, double *const *d_peers = nullptr, int n_peers = 0,
-           int64_t rec_row0 = 0)
+           int64_t rec_row0 = 0, const int32_t *d_order = nullptr)
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
@@ -214,7 +228,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.queue = h->queue + (h->launches % kQueueRing);
     a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
     a.executed = h->executed;
-    a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived;
+    a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived; a.order = d_order;
     a.peers = d_peers; a.n_peers = n_peers; a.rec_row0 = rec_row0;
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
@@ -281,8 +295,17 @@ int icpb_create(int device, icpb_handle *out)
     for (int k = 0; k < 16 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->seg_ev[k], cudaEventDisableTiming);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->done_ev[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&h->arrived_dev, sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaHostAlloc(&h->seg_vals_pinned, sizeof(int32_t) * 32, cudaHostAllocDefault);
-    if (e == cudaSuccess) for (int k = 0; k < 32; ++k) h->seg_vals_pinned[k] = k;
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->seg_vals_pinned, sizeof(int32_t) * (kMaxSegments + 1), cudaHostAllocDefault);
+    if (e == cudaSuccess) for (int k = 0; k <= kMaxSegments; ++k) h->seg_vals_pinned[k] = k;
+    if (e == cudaSuccess && !getenv("ICPB_FLAG_COPY")) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fp, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            h->write32 = (int (*)(cudaStream_t, unsigned long long, unsigned int, unsigned int))fp;
+        else
+            cudaGetLastError();
+    }
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "icpb_create: %s", cudaGetErrorString(e));
         if (h->queue) cudaFree(h->queue);
@@ -459,11 +482,15 @@ int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, i
 /* Upload + align with the upload hidden behind the kernels: the scan table goes up in segments on
  * the copy stream; pairs are grouped by the segment that completes them (the larger of their two
  * scan ids) and every group is launched as soon as its segment has arrived. */
-int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
-                    const int32_t *h_pairs, const double *h_init, int64_t B, const icpb_params *p,
-                    double *h_T, double *h_err, int32_t *h_passes)
+int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                       const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                       const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes)
 {
     if (!h || !h_xy || !h_offsets || n_scans <= 0) return fail(ICPB_EINVAL, "icpb_align_host: bad argument%s");
+    if ((init_ld != 6 && init_ld != 9) || (T_ld != 6 && T_ld != 9))
+        return fail(ICPB_EINVAL, "icpb_align_host: init_ld / T_ld must be 6 (2x3 rows) or 9 (3x3)%s");
+    static const bool trace = getenv("ICPB_TRACE") != nullptr;
+    const double t_entry = trace ? now_us() : 0.0;
     int rc = check_params(p, B);
     if (rc) return rc;
     if (p->pair_mode != 0 || p->hist_cap > 0 || p->corr_stride > 0)
@@ -471,8 +498,25 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
     int64_t longest = 0;
     if ((rc = validate_offsets(h_offsets, n_scans, &longest))) return rc;
     if (B > 0 && (!h_pairs || !h_T || !h_err || !h_passes)) return fail(ICPB_EINVAL, "null pointer%s");
-    for (int64_t b = 0; b < 2 * B; ++b)
-        if (h_pairs[b] < 0 || h_pairs[b] >= n_scans) return fail(ICPB_EINVAL, "pair index out of range%s");
+    {
+        int32_t lo = 0, hi = 0;                               // branch-free range check
+        for (int64_t b = 0; b < 2 * B; ++b) { lo = h_pairs[b] < lo ? h_pairs[b] : lo; hi = h_pairs[b] > hi ? h_pairs[b] : hi; }
+        if (lo < 0 || hi >= n_scans) return fail(ICPB_EINVAL, "pair index out of range%s");
+    }
+    if (h_init && B > 0) {                                    // before any state of the handle changes
+        for (int64_t b = 0; b < B && init_ld == 9; ++b) {
+            const double *m = h_init + 9 * b;
+            if (!(m[6] == 0.0 && m[7] == 0.0 && m[8] == 1.0))
+                return fail(ICPB_EINVAL, "transform bottom row must be [0, 0, 1] (an SE(2) matrix)%s");
+        }
+        uint64_t bad = 0;                                     // all-ones exponent = inf or NaN; integer test, vectorises
+        for (int64_t k = 0; k < (int64_t)init_ld * B; ++k) {
+            uint64_t u;
+            memcpy(&u, h_init + k, sizeof u);
+            bad |= (uint64_t)((u & 0x7ff0000000000000ULL) == 0x7ff0000000000000ULL);
+        }
+        if (bad) return fail(ICPB_EINVAL, "transform holds non-finite values%s");
+    }
     CU(cudaSetDevice(h->device));
     const size_t nb_xy = sizeof(double) * 2 * (size_t)h_offsets[n_scans];
     const size_t nb_off = sizeof(int64_t) * (size_t)(n_scans + 1);
@@ -486,69 +530,104 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
         CU(cudaStreamSynchronize(h->stream));
         return 0;
     }
-    // segments of roughly equal size: enough of them that the first kernels start early, few
-    // enough that every group still fills the GPU (a group of a few hundred pairs would not)
-    int nseg = (int)(nb_xy / (4u << 20)) + 1;                // ~4 MB pieces: the first pairs start after ~0.1 ms
+    // Segments of the scan table: equal pieces of about 4 MB, at most 16 (the first pairs start ~0.1 ms
+    // into the upload; the kernel is launched before any piece has arrived and its CTAs wait on the
+    // counter).  Measured on the 81 MB chain table: 4 pieces 2.49 ms, 16 2.35 ms, 32 2.55 ms, 64 2.86 ms
+    // per call -- every 4-byte counter copy costs the copy engine ~6 us.
+    const int64_t total = h_offsets[n_scans];
+    int nseg = (int)(nb_xy / (4u << 20)) + 1;
     if (nseg > 16) nseg = 16;
     if (const char *t = getenv("ICPB_SEGMENTS")) {          // tuning experiments only
         const int v = atoi(t);
-        if (v >= 1 && v <= 16) nseg = v;
+        if (v >= 1 && v <= kMaxSegments) nseg = v;
     }
     if (nseg > n_scans) nseg = (int)n_scans;
-    std::vector<int64_t> seg_end(nseg);                       // exclusive scan id
+    // A piece must end on a 32-byte sector boundary (an even point offset): the kernel reads scans
+    // through L1, and a sector that straddled two pieces could be cached while its second half had
+    // not arrived yet.  Boundaries on a 128-byte line (offset % 8 == 0) are preferred when one is near.
+    int64_t seg_end[kMaxSegments];                            // exclusive scan id
     {
-        const int64_t total = h_offsets[n_scans];
         int64_t s = 0;
-        for (int k = 0; k < nseg; ++k) {
+        int made = 0;
+        for (int k = 0; k < nseg - 1; ++k) {
             const int64_t want = total * (k + 1) / nseg;
             while (s < n_scans && h_offsets[s] < want) ++s;
-            if (k == nseg - 1) s = n_scans;
-            seg_end[k] = s > 0 ? s : 1;
+            int64_t pick = -1;
+            for (int64_t c = s; c < n_scans && c < s + 64; ++c) {
+                if (h_offsets[c] % 8 == 0) { pick = c; break; }
+                if (pick < 0 && h_offsets[c] % 2 == 0) pick = c;
+            }
+            if (pick <= 0 || pick >= n_scans || (made > 0 && pick <= seg_end[made - 1])) continue;   // merge with the next piece
+            seg_end[made++] = pick;
+            s = pick;
+        }
+        seg_end[made++] = n_scans;
+        nseg = made;
+    }
+    // pinned staging, 8-byte members first:  up = [init | pairs | seg | order],  down = [T | err | passes]
+    const size_t nbI = sizeof(double) * 6 * (size_t)B, nbE = sizeof(double) * (size_t)B, nb4 = sizeof(int32_t) * (size_t)B;
+    const size_t nb_up = nbI + 4 * nb4, nb_down = nbI + nbE + nb4;
+    if ((rc = h->stage.reserve(nb_up + nb_down))) return rc;
+    if ((rc = h->s_init.reserve(nb_up))) return rc;
+    if ((rc = h->s_T.reserve(nb_down))) return rc;
+    double *pinit = (double *)h->stage.p;
+    int32_t *ppairs = (int32_t *)(pinit + 6 * B), *pseg = ppairs + 2 * B, *porder = pseg + B;
+    double *tT = (double *)((char *)h->stage.p + nb_up), *tE = tT + 6 * B;
+    int32_t *tP = (int32_t *)(tE + B);
+    double *d_init = (double *)h->s_init.p;
+    int32_t *d_pairs = (int32_t *)(d_init + 6 * B), *d_seg = d_pairs + 2 * B, *d_order = d_seg + B;
+    double *d_T = (double *)h->s_T.p, *d_err = d_T + 6 * B;
+    int32_t *d_passes = (int32_t *)(d_err + B);
+    // Queue order: pairs grouped by the segment that completes them; the pairs, initial guesses and
+    // results themselves stay in the caller's order.  A batch that already comes in arrival order
+    // (the odometry chain does) needs no permutation at all.
+    bool in_order = true;
+    {
+        std::vector<int32_t> seg_of_scan((size_t)n_scans);
+        for (int64_t s = 0, k = 0; s < n_scans; ++s) { while (s >= seg_end[k]) ++k; seg_of_scan[s] = (int32_t)k; }
+        int32_t *seg_of_pair = tP;                            // scratch: the download area is free until the end
+        int32_t prev = 0, sorted = 1;
+        for (int64_t b = 0; b < B; ++b) {
+            const int32_t i = h_pairs[2 * b], j = h_pairs[2 * b + 1];
+            const int32_t sg = seg_of_scan[i > j ? i : j];
+            seg_of_pair[b] = sg;
+            sorted &= (int32_t)(sg >= prev);
+            prev = sg;
+        }
+        in_order = sorted != 0;
+        if (in_order) {
+            memcpy(pseg, seg_of_pair, nb4);
+        } else {                                              // stable counting sort
+            int64_t start[kMaxSegments + 1] = {0};
+            for (int64_t b = 0; b < B; ++b) ++start[seg_of_pair[b] + 1];
+            for (int k = 0; k < nseg; ++k) start[k + 1] += start[k];
+            for (int64_t b = 0; b < B; ++b) {
+                const int64_t q = start[seg_of_pair[b]]++;
+                porder[q] = (int32_t)b; pseg[q] = seg_of_pair[b];
+            }
         }
     }
-    // group pairs by completing segment (stable counting sort)
-    std::vector<int32_t> seg_of_scan((size_t)n_scans);
-    for (int64_t s = 0, k = 0; s < n_scans; ++s) { while (s >= seg_end[k]) ++k; seg_of_scan[s] = (int32_t)k; }
-    std::vector<int64_t> start(nseg + 1, 0);
-    std::vector<int32_t> seg_of_pair((size_t)B);
-    for (int64_t b = 0; b < B; ++b) {
-        const int32_t m = h_pairs[2 * b] > h_pairs[2 * b + 1] ? h_pairs[2 * b] : h_pairs[2 * b + 1];
-        seg_of_pair[b] = seg_of_scan[m];
-        ++start[seg_of_pair[b] + 1];
+    memcpy(ppairs, h_pairs, 2 * nb4);
+    if (h_init) {
+        if (init_ld == 6) {
+            memcpy(pinit, h_init, nbI);
+        } else {
+            for (int64_t b = 0; b < B; ++b) memcpy(pinit + 6 * b, h_init + 9 * b, 6 * sizeof(double));
+        }
     }
-    for (int k = 0; k < nseg; ++k) start[k + 1] += start[k];
-    std::vector<int64_t> perm((size_t)B), fill(start.begin(), start.end() - 1);
-    for (int64_t b = 0; b < B; ++b) perm[fill[seg_of_pair[b]]++] = b;
-    const size_t nbP = sizeof(int32_t) * 2 * (size_t)B, nbI = sizeof(double) * 6 * (size_t)B;
-    // pinned staging: [T | init | err | pairs | passes | seg], 8-byte members first
-    if ((rc = h->stage.reserve(2 * nbI + sizeof(double) * (size_t)B + nbP + 2 * sizeof(int32_t) * (size_t)B))) return rc;
-    double *tT = (double *)h->stage.p, *pinit = tT + 6 * B, *tE = pinit + 6 * B;
-    int32_t *ppairs = (int32_t *)(tE + B), *tP = ppairs + 2 * B, *pseg = tP + B;
-    for (int64_t q = 0; q < B; ++q) {
-        const int64_t b = perm[q];
-        ppairs[2 * q] = h_pairs[2 * b]; ppairs[2 * q + 1] = h_pairs[2 * b + 1];
-        pseg[q] = seg_of_pair[b];
-        if (h_init) memcpy(pinit + 6 * q, h_init + 6 * b, 6 * sizeof(double));
-    }
-    if ((rc = h->s_pairs.reserve(nbP))) return rc;
-    if (h_init && (rc = h->s_init.reserve(nbI))) return rc;
-    if ((rc = h->s_T.reserve(nbI))) return rc;
-    if ((rc = h->s_err.reserve(sizeof(double) * (size_t)B))) return rc;
-    if ((rc = h->s_passes.reserve(sizeof(int32_t) * (size_t)B))) return rc;
+    const double t_prep = trace ? now_us() : 0.0;
     cudaStream_t cp = h->stream, cs = h->cstream[0];
-    if ((rc = h->s_seg.reserve(sizeof(int32_t) * (size_t)B))) return rc;
     CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
     CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
-    CU(cudaMemcpyAsync(h->s_pairs.p, ppairs, nbP, cudaMemcpyHostToDevice, cp));
-    CU(cudaMemcpyAsync(h->s_seg.p, pseg, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, cp));
-    if (h_init) CU(cudaMemcpyAsync(h->s_init.p, pinit, nbI, cudaMemcpyHostToDevice, cp));
+    const size_t nb_idx = (in_order ? 3 : 4) * nb4;           // pairs, seg (, order)
+    if (h_init) CU(cudaMemcpyAsync(d_init, pinit, nbI + nb_idx, cudaMemcpyHostToDevice, cp));
+    else        CU(cudaMemcpyAsync(d_pairs, ppairs, nb_idx, cudaMemcpyHostToDevice, cp));
     CU(cudaEventRecord(h->seg_ev[0], cp));
     // ONE launch over all pairs, in arrival order; its CTAs wait on the segment counter
     CU(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
-    rc = launch(h, h->xy, h->offsets, n_scans, longest, (const int32_t *)h->s_pairs.p,
-                h_init ? (const double *)h->s_init.p : nullptr, B, p,
-                (double *)h->s_T.p, (double *)h->s_err.p, (int32_t *)h->s_passes.p,
-                nullptr, nullptr, cs, B, (const int32_t *)h->s_seg.p, h->arrived_dev);
+    rc = launch(h, h->xy, h->offsets, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
+                d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, nullptr, 0, 0,
+                in_order ? nullptr : d_order);
     if (rc) return rc;
     int64_t s_prev = 0;
     for (int k = 0; k < nseg; ++k) {
@@ -556,23 +635,39 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
         if (o1 > o0)
             CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
                                cudaMemcpyHostToDevice, cp));
-        // stream order: the flag lands after the segment it announces
-        CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+        // stream order: the counter changes after the segment it announces has landed
+        if (!h->write32 || h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0)
+            CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
         s_prev = seg_end[k];
     }
     CU(cudaEventRecord(h->done_ev[0], cs));
     CU(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
-    CU(cudaMemcpyAsync(tT, h->s_T.p, nbI, cudaMemcpyDeviceToHost, cp));
-    CU(cudaMemcpyAsync(tE, h->s_err.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, cp));
-    CU(cudaMemcpyAsync(tP, h->s_passes.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, cp));
+    CU(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+    const double t_enq = trace ? now_us() : 0.0;
     CU(cudaStreamSynchronize(cp));
-    for (int64_t q = 0; q < B; ++q) {
-        const int64_t b = perm[q];
-        memcpy(h_T + 6 * b, tT + 6 * q, 6 * sizeof(double));
-        h_err[b] = tE[q];
-        h_passes[b] = tP[q];
+    const double t_sync = trace ? now_us() : 0.0;
+    if (T_ld == 6) {
+        memcpy(h_T, tT, nbI);
+    } else {
+        for (int64_t b = 0; b < B; ++b) {
+            double *m = h_T + 9 * b;
+            memcpy(m, tT + 6 * b, 6 * sizeof(double));
+            m[6] = 0.0; m[7] = 0.0; m[8] = 1.0;
+        }
     }
+    memcpy(h_err, tE, nbE);
+    memcpy(h_passes, tP, nb4);
+    if (trace)
+        fprintf(stderr, "[icpb_align_host] prep %.0f us, enqueue %.0f us, wait %.0f us, scatter %.0f us (%d segments)\n",
+                t_prep - t_entry, t_enq - t_prep, t_sync - t_enq, now_us() - t_sync, nseg);
     return 0;
+}
+
+int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                    const int32_t *h_pairs, const double *h_init, int64_t B, const icpb_params *p,
+                    double *h_T, double *h_err, int32_t *h_passes)
+{
+    return icpb_align_host_ld(h, h_xy, h_offsets, n_scans, h_pairs, h_init, 6, B, p, h_T, 6, h_err, h_passes);
 }
 
 int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,

@@ -52,8 +52,9 @@ struct KernelArgs {
     unsigned long long *executed; // optional: += distance evaluations actually executed
     // streaming upload (icpb_align_host): pair b may start once *arrived > seg_of_pair[b], i.e. the
     // copy engine has delivered the scan-table segment holding the later of its two scans
-    const int32_t *seg_of_pair;
+    const int32_t *seg_of_pair;      // by queue position
     const volatile int32_t *arrived;
+    const int32_t *order;            // queue position -> pair id (nullptr: identity)
     // fused gather (multi-GPU): every finished pair's 8-double constraint record
     // [T(6), error, passes] is stored straight into every rank's gather buffer over NVLink peer
     // memory, at row rec_row0 + pair id; peers[r] is rank r's buffer as mapped in this process
@@ -327,18 +328,20 @@ icp_align_kernel(const KernelArgs a)
             s_tile_ctr[0] = 0; s_tile_ctr[1] = 0;
         }
         sync_all();
-        const int64_t pid = s_pid;
-        if (pid >= a.B) break;
+        const int64_t qpos = s_pid;
+        if (qpos >= a.B) break;
+        const int64_t pid = a.order ? (int64_t)a.order[qpos] : qpos;
         if (a.arrived) {
             // wait for the copy engine (a DMA on another stream, not another kernel): the queue hands
             // pairs out in arrival order, so only the CTAs at the front of the upload ever wait
             if (tid == 0) {
-                const int need = a.seg_of_pair[pid];
+                const int need = a.seg_of_pair[qpos];
                 const long long t0 = clock64();
                 while (*a.arrived <= need) {
                     __nanosleep(256);
                     if (clock64() - t0 > (1LL << 33)) break;      // ~4 s: never hang the GPU on a failed copy
                 }
+                __threadfence();                                 // the scans are read after the counter
             }
             __syncthreads();
         }

@@ -242,25 +242,24 @@ class IcpEngine:
             pairs_a = pairs_a.reshape(0, 2)
         if pairs_a.ndim != 2 or pairs_a.shape[1] != 2:
             raise ValueError(f"pairs has shape {pairs_a.shape}; expected (B, 2) of (source, target) scan ids")
-        if pairs_a.size and (pairs_a.min() < 0 or pairs_a.max() >= table.n_scans):
-            raise ValueError("pair index out of range")
         B = len(pairs_a)
         p.k_block = max(B, 1)
-        init6 = None
+        init33 = None
         if init_transforms is not None:
-            it = np.asarray(init_transforms, dtype=np.float64)
-            if it.shape != (B, 3, 3):
-                raise ValueError(f"init_transforms has shape {it.shape}; expected ({B}, 3, 3)")
-            init6 = _to6(it)
-        T6 = np.empty((B, 6))
+            # the reference's (B, 3, 3) matrices go to the library as they are: it checks the pair
+            # indices, the bottom rows and finiteness while it stages them (ICPB_EINVAL -> ValueError)
+            init33 = np.ascontiguousarray(init_transforms, dtype=np.float64)
+            if init33.shape != (B, 3, 3):
+                raise ValueError(f"init_transforms has shape {init33.shape}; expected ({B}, 3, 3)")
+        T33 = np.empty((B, 3, 3))
         err = np.empty(B)
         passes = np.empty(B, dtype=np.int32)
-        _lib.check(self._L.icpb_align_host(self._h, _ptr(table.xy), _ptr(table.offsets), table.n_scans,
-                                           _ptr(pairs_a), _ptr(init6), B, ctypes.byref(p),
-                                           _ptr(T6), _ptr(err), _ptr(passes)), "icpb_align_host")
+        _lib.check(self._L.icpb_align_host_ld(self._h, _ptr(table.xy), _ptr(table.offsets), table.n_scans,
+                                              _ptr(pairs_a), _ptr(init33), 9, B, ctypes.byref(p),
+                                              _ptr(T33), 9, _ptr(err), _ptr(passes)), "icpb_align_host")
         self.table = table
         self._keep = None
-        return BatchResult(_to33(T6), err, passes, None, None)
+        return BatchResult(T33, err, passes, None, None)
 
     # -- device-buffer run (inputs and outputs resident in HBM; torch tensors) ---------------
     def run_device(self, pairs_t, init_t, out_T, out_err, out_passes, epsilon=0.01, max_iters=100,

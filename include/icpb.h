@@ -128,6 +128,14 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
                     const int32_t *h_pairs, const double *h_init, int64_t B, const icpb_params *p,
                     double *h_T, double *h_err, int32_t *h_passes);
 
+/* The same with the transforms in the caller's own layout: init_ld / T_ld = 9 reads and writes the
+ * reference's full 3x3 row-major matrices (what scripts/main.py:244 passes and src/icp.py:97
+ * returns; the bottom row is checked to be [0, 0, 1] on the way in and written on the way out),
+ * 6 the packed top two rows.  Non-finite initial guesses are rejected (ICPB_EINVAL). */
+int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                       const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                       const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes);
+
 /* One pair given directly as two (n, 2) float64 host arrays: the reference's
  * icp(pc1, pc2, init_transform, epsilon, max_iters, stopping_thresh, rotation_only)
  * (src/icp.py:72) and, with epsilon = +inf (one pass), icp_iteration() (src/icp.py:55-69). */

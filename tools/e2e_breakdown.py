@@ -19,6 +19,6 @@ print("run only (resident scans) %.3f ms" % tm(lambda: e.run(pairs, init, epsilo
 print("set_scans only (pinned)   %.3f ms" % tm(lambda: e.set_scans(tp)))
 print("_to6(init)                %.3f ms" % tm(lambda: gicp._to6(init)))
 print("_to33                     %.3f ms" % tm(lambda: gicp._to33(np.zeros((4999, 6)))))
-for sg in (1, 2, 4):
+for sg in (4, 16, 32, 64):
     os.environ["ICPB_SEGMENTS"] = str(sg)
     print("align segments=%d          %.3f ms" % (sg, tm(lambda: e.align(tp, pairs, init, epsilon=0.05))))
