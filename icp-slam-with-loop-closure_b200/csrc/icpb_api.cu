@@ -212,7 +212,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
            cudaStream_t stream, int64_t B_total = 0, const int32_t *d_seg_of_pair = nullptr,
            const int32_t *d_arrived = nullptr, double *const *d_peers = nullptr, int n_peers = 0,
-           int64_t rec_row0 = 0, const int32_t *d_order = nullptr)
+           int64_t rec_row0 = 0, const int32_t *d_order = nullptr, int32_t *d_upload_timeout = nullptr)
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
@@ -228,7 +228,7 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.queue = h->queue + (h->launches % kQueueRing);
     a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
     a.executed = h->executed;
-    a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived; a.order = d_order;
+    a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived; a.order = d_order; a.upload_timeout = d_upload_timeout;
     a.peers = d_peers; a.n_peers = n_peers; a.rec_row0 = rec_row0;
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
@@ -566,7 +566,7 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     }
     // pinned staging, 8-byte members first:  up = [init | pairs | seg | order],  down = [T | err | passes]
     const size_t nbI = sizeof(double) * 6 * (size_t)B, nbE = sizeof(double) * (size_t)B, nb4 = sizeof(int32_t) * (size_t)B;
-    const size_t nb_up = nbI + 4 * nb4, nb_down = nbI + nbE + nb4;
+    const size_t nb_up = nbI + 4 * nb4, nb_down = nbI + nbE + nb4 + sizeof(int32_t);   // + the "upload timed out" word
     if ((rc = h->stage.reserve(nb_up + nb_down))) return rc;
     if ((rc = h->s_init.reserve(nb_up))) return rc;
     if ((rc = h->s_T.reserve(nb_down))) return rc;
@@ -618,6 +618,7 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     const double t_prep = trace ? now_us() : 0.0;
     cudaStream_t cp = h->stream, cs = h->cstream[0];
     CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
+    CU(cudaMemsetAsync(d_passes + B, 0, sizeof(int32_t), cp));
     CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
     const size_t nb_idx = (in_order ? 3 : 4) * nb4;           // pairs, seg (, order)
     if (h_init) CU(cudaMemcpyAsync(d_init, pinit, nbI + nb_idx, cudaMemcpyHostToDevice, cp));
@@ -627,17 +628,21 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     CU(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
     rc = launch(h, h->xy, h->offsets, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
                 d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, nullptr, 0, 0,
-                in_order ? nullptr : d_order);
+                in_order ? nullptr : d_order, d_passes + B);
     if (rc) return rc;
     int64_t s_prev = 0;
+    const bool drop_counter = getenv("ICPB_TEST_DROP_COUNTER") != nullptr;
     for (int k = 0; k < nseg; ++k) {
         const int64_t o0 = h_offsets[s_prev], o1 = h_offsets[seg_end[k]];
         if (o1 > o0)
             CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
                                cudaMemcpyHostToDevice, cp));
         // stream order: the counter changes after the segment it announces has landed
-        if (!h->write32 || h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0)
+        if (drop_counter) {
+            // tests only: the kernel must time out and the batch be rerun
+        } else if (!h->write32 || h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0) {
             CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+        }
         s_prev = seg_end[k];
     }
     CU(cudaEventRecord(h->done_ev[0], cs));
@@ -645,6 +650,15 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     CU(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
     const double t_enq = trace ? now_us() : 0.0;
     CU(cudaStreamSynchronize(cp));
+    if (tP[B] != 0) {
+        // a CTA gave up waiting for its scans (see the kernel): by now the whole table is resident,
+        // so run the batch again without the streaming protocol
+        rc = launch(h, h->xy, h->offsets, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
+                    d_T, d_err, d_passes, nullptr, nullptr, cp);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+        CU(cudaStreamSynchronize(cp));
+    }
     const double t_sync = trace ? now_us() : 0.0;
     if (T_ld == 6) {
         memcpy(h_T, tT, nbI);

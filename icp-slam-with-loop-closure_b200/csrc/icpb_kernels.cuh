@@ -55,6 +55,7 @@ struct KernelArgs {
     const int32_t *seg_of_pair;      // by queue position
     const volatile int32_t *arrived;
     const int32_t *order;            // queue position -> pair id (nullptr: identity)
+    int32_t *upload_timeout;         // set to 1 if a wait on `arrived` gave up (the host then reruns the batch)
     // fused gather (multi-GPU): every finished pair's 8-double constraint record
     // [T(6), error, passes] is stored straight into every rank's gather buffer over NVLink peer
     // memory, at row rec_row0 + pair id; peers[r] is rank r's buffer as mapped in this process
@@ -339,7 +340,11 @@ icp_align_kernel(const KernelArgs a)
                 const long long t0 = clock64();
                 while (*a.arrived <= need) {
                     __nanosleep(256);
-                    if (clock64() - t0 > (1LL << 33)) break;      // ~4 s: never hang the GPU on a failed copy
+                    // never hang the GPU on a copy that does not come (a profiler that serialises the
+                    // kernel against the copy stream, a failed transfer): give up after ~0.5 s, once for
+                    // the whole grid, and tell the host, which reruns the batch on the resident table
+                    if (*(volatile int32_t *)a.upload_timeout) break;
+                    if (clock64() - t0 > (1LL << 30)) { *(volatile int32_t *)a.upload_timeout = 1; break; }
                 }
                 __threadfence();                                 // the scans are read after the counter
             }

@@ -309,6 +309,49 @@ def test_pipelined_align_equals_upload_then_run(gicp):
     e.close()
 
 
+def test_align_in_order_batch_and_bad_inputs(gicp):
+    """A batch already in arrival order (the odometry chain) takes the path without a queue-order
+    array; bad pair indices, bottom rows and non-finite guesses are rejected by the library itself
+    (ICPB_EINVAL -> ValueError) before any state of the handle changes."""
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(700, 720, seed=5)            # ~8 MB: 3 pieces
+    e = gicp.IcpEngine()
+    a = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
+    e.set_scans(scans)
+    b = e.run(pairs, init, epsilon=0.05, max_iters=30)
+    np.testing.assert_array_equal(a.T, b.T)
+    np.testing.assert_array_equal(a.iters, b.iters)
+    assert np.all(a.T[:, 2, :] == [0.0, 0.0, 1.0])
+    bad = init.copy(); bad[3, 2, 0] = 0.5
+    with pytest.raises(ValueError):
+        e.align(scans, pairs, bad)
+    bad = init.copy(); bad[5, 0, 2] = np.inf
+    with pytest.raises(ValueError):
+        e.align(scans, pairs, bad)
+    bp = pairs.copy(); bp[7, 1] = len(scans)
+    with pytest.raises(ValueError):
+        e.align(scans, bp, init)
+    c = e.run(pairs[:10], init[:10], epsilon=0.05, max_iters=30)                      # the table is still usable
+    np.testing.assert_array_equal(c.T, b.T[:10])
+    e.close()
+
+
+def test_align_survives_a_missing_arrival_counter(gicp, monkeypatch):
+    """If the 'piece k has arrived' counter never moves (a profiler serialising the kernel against the
+    copy stream, a failed transfer), the waiting CTAs give up after ~0.5 s, flag it, and the library
+    reruns the batch on the by then resident table: same results, no hang."""
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(120, 360, seed=6)
+    e = gicp.IcpEngine()
+    ref = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
+    monkeypatch.setenv("ICPB_TEST_DROP_COUNTER", "1")
+    got = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
+    monkeypatch.delenv("ICPB_TEST_DROP_COUNTER")
+    np.testing.assert_array_equal(got.T, ref.T)
+    np.testing.assert_array_equal(got.iters, ref.iters)
+    e.close()
+
+
 def test_helper_functions(gicp, c_oracle):
     """get_transform / get_error / get_correspondences / get_closest_point (src/icp.py:4-52)."""
     from oracle import icp_oracle as po
