@@ -86,8 +86,16 @@ def lib() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(SO_PATH):
-        raise IcpbError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                        "(there is no CPU fallback)")
+        # a fresh checkout (the library is not in the history): compile the CUDA library once, in-tree;
+        # if that is impossible there is nothing to fall back to
+        import shutil
+        if "ICPB_SO" in os.environ or shutil.which("nvcc") is None:
+            raise IcpbError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        try:
+            build()
+        except (subprocess.CalledProcessError, OSError) as exc:
+            raise IcpbError(f"{SO_PATH} is missing and could not be built ({exc}); there is no CPU fallback") from exc
     L = ctypes.CDLL(SO_PATH)
     vp, i64, i32p, dp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p
     L.icpb_default_params.argtypes = [ctypes.POINTER(IcpbParams)]
