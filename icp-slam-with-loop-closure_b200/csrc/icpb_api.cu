@@ -578,6 +578,30 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     int32_t *d_pairs = (int32_t *)(d_init + 6 * B), *d_seg = d_pairs + 2 * B, *d_order = d_seg + B;
     double *d_T = (double *)h->s_T.p, *d_err = d_T + 6 * B;
     int32_t *d_passes = (int32_t *)(d_err + B);
+    // The first pieces start NOW, before the per-pair staging below: the copy engine works while the
+    // host sorts and packs (everything has been validated above; nothing below can fail on user input).
+    cudaStream_t cp = h->stream, cp2 = h->cstream[1], cs = h->cstream[0];
+    const bool drop_counter = getenv("ICPB_TEST_DROP_COUNTER") != nullptr;
+    int64_t s_prev = 0;
+    auto enqueue_piece = [&](int k) -> int {
+        const int64_t o0 = h_offsets[s_prev], o1 = h_offsets[seg_end[k]];
+        if (o1 > o0)
+            CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
+                               cudaMemcpyHostToDevice, cp));
+        // stream order: the counter changes after the segment it announces has landed
+        if (drop_counter) {
+            // tests only: the kernel must time out and the batch be rerun
+        } else if (!h->write32 || h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0) {
+            CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+        }
+        s_prev = seg_end[k];
+        return 0;
+    };
+    CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
+    CU(cudaEventRecord(h->seg_ev[1], cp));                    // the counter is zero before the kernel may start
+    const int n_early = nseg < 4 ? nseg : 4;
+    for (int k = 0; k < n_early; ++k)
+        if ((rc = enqueue_piece(k))) return rc;
     // Queue order: pairs grouped by the segment that completes them; the pairs, initial guesses and
     // results themselves stay in the caller's order.  A batch that already comes in arrival order
     // (the odometry chain does) needs no permutation at all.
@@ -616,35 +640,22 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
         }
     }
     const double t_prep = trace ? now_us() : 0.0;
-    cudaStream_t cp = h->stream, cs = h->cstream[0];
-    CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
-    CU(cudaMemsetAsync(d_passes + B, 0, sizeof(int32_t), cp));
-    CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
+    // the small per-pair block goes up on a second copy stream, beside the pieces already in flight
+    CU(cudaMemsetAsync(d_passes + B, 0, sizeof(int32_t), cp2));
+    CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp2));
     const size_t nb_idx = (in_order ? 3 : 4) * nb4;           // pairs, seg (, order)
-    if (h_init) CU(cudaMemcpyAsync(d_init, pinit, nbI + nb_idx, cudaMemcpyHostToDevice, cp));
-    else        CU(cudaMemcpyAsync(d_pairs, ppairs, nb_idx, cudaMemcpyHostToDevice, cp));
-    CU(cudaEventRecord(h->seg_ev[0], cp));
+    if (h_init) CU(cudaMemcpyAsync(d_init, pinit, nbI + nb_idx, cudaMemcpyHostToDevice, cp2));
+    else        CU(cudaMemcpyAsync(d_pairs, ppairs, nb_idx, cudaMemcpyHostToDevice, cp2));
+    CU(cudaEventRecord(h->seg_ev[0], cp2));
     // ONE launch over all pairs, in arrival order; its CTAs wait on the segment counter
     CU(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
+    CU(cudaStreamWaitEvent(cs, h->seg_ev[1], 0));
     rc = launch(h, h->xy, h->offsets, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
                 d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, nullptr, 0, 0,
                 in_order ? nullptr : d_order, d_passes + B);
-    if (rc) return rc;
-    int64_t s_prev = 0;
-    const bool drop_counter = getenv("ICPB_TEST_DROP_COUNTER") != nullptr;
-    for (int k = 0; k < nseg; ++k) {
-        const int64_t o0 = h_offsets[s_prev], o1 = h_offsets[seg_end[k]];
-        if (o1 > o0)
-            CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
-                               cudaMemcpyHostToDevice, cp));
-        // stream order: the counter changes after the segment it announces has landed
-        if (drop_counter) {
-            // tests only: the kernel must time out and the batch be rerun
-        } else if (!h->write32 || h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0) {
-            CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
-        }
-        s_prev = seg_end[k];
-    }
+    if (rc) { cudaStreamSynchronize(cp); cudaStreamSynchronize(cp2); return rc; }
+    for (int k = n_early; k < nseg; ++k)
+        if ((rc = enqueue_piece(k))) { cudaStreamSynchronize(cp); cudaStreamSynchronize(cs); return rc; }
     CU(cudaEventRecord(h->done_ev[0], cs));
     CU(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
     CU(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
