@@ -119,3 +119,25 @@ def test_pipeline_tool_runs_end_to_end():
     assert set(r["stage_ms"]) == {"scan_matching", "loop_closure", "optimisation", "orientation", "occupancy_grid"}
     assert r["chain_pairs"] == 399 and r["grid"][0] > 50 and r["grid"][1] > 50
     assert np.isfinite(r["ate_m"]["scan_matching"]) and np.isfinite(r["ate_m"]["optimised"])
+
+
+def test_reference_fan_out_with_loky_workers(monkeypatch):
+    """The reference's own fan-out, unchanged except for the import: joblib/loky worker processes
+    unpickle ``icp.icp`` by its qualified name and each creates its CUDA handle on first use
+    (scripts/main.py:240-247).  The results equal the one-launch ``icp_batch`` bit for bit."""
+    from joblib import Parallel, delayed
+    from icp_slam_b200 import icp, synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    scans, pairs, init, _, _ = synth.make_chain_workload(13, 360, seed=467200)
+    out = Parallel(n_jobs=2, backend="loky")(
+        delayed(icp.icp)(np.c_[scans[i], np.ones(len(scans[i]))], np.c_[scans[j], np.ones(len(scans[j]))],
+                         init_transform=init[k], max_iters=100, epsilon=0.05)
+        for k, (i, j) in enumerate(pairs))
+    res = icp.icp_batch(scans, pairs, init, max_iters=100, epsilon=0.05)
+    assert len(out) == len(pairs)
+    for k, (tfs, err) in enumerate(out):
+        assert len(tfs) == res.iters[k] + 1
+        np.testing.assert_array_equal(tfs[0], init[k])
+        np.testing.assert_array_equal(tfs[-1], res.T[k])
+        assert err == res.error[k]
