@@ -36,8 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 4,999-pair chain, from the
-# committed `ncu --set full` capture (profiles/r01j_align_ncu_full_summary.csv); None until measured
-TRAFFIC_NCU = 84.3e6   # 81.1 MB read (= one pass over the 81 MB scan table) + 3.2 MB written
+# committed `ncu --set full` capture (profiles/r01m_align_ncu_full_summary.csv); None until measured
+TRAFFIC_NCU = 85.1e6   # 81.1 MB read (= one pass over the 81 MB scan table) + 4.0 MB written
 METRIC = "icp_scan_pair_alignments_per_sec"
 UNIT = "pairs/s"
 SEED = 467002
