@@ -54,6 +54,24 @@ def odometry_chain(lidar_points, odometry, max_iters=100, epsilon=0.05, device=N
     return compose_chain(odometry[0], res.T), res
 
 
+def odometry_chain_strided(lidar_points, odometry, start, skip, max_iters=100, epsilon=0.05, device=None):
+    """The serial stride-k scan matching loop of scripts/map_icp.py:44-86 (same loop in
+    scripts/map_proximity_loop_closure.py:50-88) as one batch: for i = start, start + skip, ... scan i
+    is aligned onto scan i - skip with the odometry difference as the initial guess, and the result is
+    composed onto the LAST pose of the list -- which for the first step is ``odometry[start - 1]``, not
+    ``odometry[start - skip]`` (the script seeds the list with the raw odometry of poses 0..start-1).
+    Returns (corrected_poses as the script builds them: (start + number of steps, 3), BatchResult)."""
+    odometry = np.asarray(odometry, dtype=np.float64)
+    if not 0 < skip < start:
+        raise ValueError("the reference asserts skip < start (scripts/map_icp.py:45)")
+    idx = np.arange(start, len(odometry), skip)
+    pairs = np.stack((idx, idx - skip), axis=1).astype(np.int32)
+    init = poses_to_mats(odometry[idx] - odometry[idx - skip])
+    res = _icp.icp_batch(lidar_points, pairs, init, epsilon=epsilon, max_iters=max_iters, device=device)
+    tail = compose_chain(odometry[start - 1], res.T)[1:]
+    return np.vstack((odometry[:start], tail)), res
+
+
 def compose_chain(pose0, transforms) -> np.ndarray:
     """Serial SE(2) prefix product of scripts/main.py:249-256:
     ``pose_i = mat_to_pose(pose_to_mat(pose_{i-1}) @ T_{i-1})``; (n + 1, 3) poses from n transforms.

@@ -141,3 +141,29 @@ def test_reference_fan_out_with_loky_workers(monkeypatch):
         np.testing.assert_array_equal(tfs[0], init[k])
         np.testing.assert_array_equal(tfs[-1], res.T[k])
         assert err == res.error[k]
+
+
+def test_strided_scan_matching_loop():
+    """callers.odometry_chain_strided = the serial loop of scripts/map_icp.py:44-86, including its
+    quirk of composing the first step onto odometry[start - 1]; checked against that loop written
+    out with the drop-in icp() and the reference's pose <-> matrix formulas (src/utils.py:28-39)."""
+    from icp_slam_b200 import callers, icp, synth
+    scans, _, _, _, odo = synth.make_chain_workload(60, 360, seed=467300)
+    start, skip = 7, 5
+
+    def pose_to_mat(p):
+        c, s = np.cos(p[2]), np.sin(p[2])
+        return np.array([[c, -s, p[0]], [s, c, p[1]], [0, 0, 1.0]])
+
+    corrected = [odo[i] for i in range(start)]
+    for i in range(start, len(odo), skip):
+        est = pose_to_mat(odo[i] - odo[i - skip])
+        tfs, _ = icp.icp(np.c_[scans[i], np.ones(len(scans[i]))], np.c_[scans[i - skip], np.ones(len(scans[i - skip]))],
+                         init_transform=est, max_iters=100, epsilon=0.05)
+        m = pose_to_mat(corrected[-1]) @ tfs[-1]
+        corrected.append(np.array([m[0, 2], m[1, 2], np.arctan2(m[1, 0], m[0, 0])]))
+    got, res = callers.odometry_chain_strided(scans, odo, start, skip)
+    assert got.shape == (len(corrected), 3) and len(res) == len(corrected) - start
+    np.testing.assert_allclose(got, np.array(corrected), rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        callers.odometry_chain_strided(scans, odo, 3, 5)
