@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
 EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destroy",
            "icpb_upload_scans", "icpb_set_scans_device", "icpb_run_device", "icpb_run_host",
            "icpb_icp_pair_host", "icpb_get_kernel_info", "icpb_launch_count", "icpb_last_error",
-           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_align_host_ld", "icpb_fit_pairs_host",
+           "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_align_host_ld", "icpb_plan_upload", "icpb_fit_pairs_host",
            "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
            "icpb_run_device_gather", "icpb_pose_graph_sgd", "icpb_occupancy_grid_bounds",
            "icpb_occupancy_grid_update"]

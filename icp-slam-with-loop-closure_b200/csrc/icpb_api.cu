@@ -482,6 +482,45 @@ int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, i
 /* Upload + align with the upload hidden behind the kernels: the scan table goes up in segments on
  * the copy stream; pairs are grouped by the segment that completes them (the larger of their two
  * scan ids) and every group is launched as soon as its segment has arrived. */
+/* Pieces of the streaming scan-table upload (pure host logic, no CUDA call).
+ * Equal pieces of about 4 MB, at most 16 by default (the first pairs start ~0.1 ms into the upload;
+ * the kernel is launched before any piece has arrived and its CTAs wait on the counter).  Measured on
+ * the 81 MB chain table with counter copies: 4 pieces 2.49 ms, 16 2.35 ms, 32 2.55 ms, 64 2.86 ms per
+ * call; with cuStreamWriteValue32 16 and 32 pieces cost the same.
+ * A piece must end on a 32-byte sector boundary (an even point offset): the kernel reads scans
+ * through L1, and a sector that straddled two pieces could be cached while its second half had not
+ * arrived yet.  Boundaries on a 128-byte line (offset % 8 == 0) are preferred when one is near; a
+ * wanted boundary with no even offset within 64 scans is dropped (its piece merges with the next). */
+int icpb_plan_upload(const int64_t *h_offsets, int64_t n_scans, int32_t pieces_wanted,
+                     int64_t *piece_end, int32_t *n_pieces)
+{
+    if (!h_offsets || n_scans <= 0 || !piece_end || !n_pieces)
+        return fail(ICPB_EINVAL, "icpb_plan_upload: bad argument%s");
+    const int64_t total = h_offsets[n_scans];
+    const size_t nb_xy = sizeof(double) * 2 * (size_t)total;
+    int nseg = (int)(nb_xy / (4u << 20)) + 1;
+    if (nseg > 16) nseg = 16;
+    if (pieces_wanted >= 1 && pieces_wanted <= kMaxSegments) nseg = pieces_wanted;
+    if (nseg > n_scans) nseg = (int)n_scans;
+    int64_t s = 0;
+    int made = 0;
+    for (int k = 0; k < nseg - 1; ++k) {
+        const int64_t want = total * (k + 1) / nseg;
+        while (s < n_scans && h_offsets[s] < want) ++s;
+        int64_t pick = -1;
+        for (int64_t c = s; c < n_scans && c < s + 64; ++c) {
+            if (h_offsets[c] % 8 == 0) { pick = c; break; }
+            if (pick < 0 && h_offsets[c] % 2 == 0) pick = c;
+        }
+        if (pick <= 0 || pick >= n_scans || (made > 0 && pick <= piece_end[made - 1])) continue;   // merge with the next piece
+        piece_end[made++] = pick;
+        s = pick;
+    }
+    piece_end[made++] = n_scans;
+    *n_pieces = made;
+    return 0;
+}
+
 int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
                        const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
                        const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes)
@@ -530,39 +569,12 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
         CU(cudaStreamSynchronize(h->stream));
         return 0;
     }
-    // Segments of the scan table: equal pieces of about 4 MB, at most 16 (the first pairs start ~0.1 ms
-    // into the upload; the kernel is launched before any piece has arrived and its CTAs wait on the
-    // counter).  Measured on the 81 MB chain table: 4 pieces 2.49 ms, 16 2.35 ms, 32 2.55 ms, 64 2.86 ms
-    // per call -- every 4-byte counter copy costs the copy engine ~6 us.
-    const int64_t total = h_offsets[n_scans];
-    int nseg = (int)(nb_xy / (4u << 20)) + 1;
-    if (nseg > 16) nseg = 16;
-    if (const char *t = getenv("ICPB_SEGMENTS")) {          // tuning experiments only
-        const int v = atoi(t);
-        if (v >= 1 && v <= kMaxSegments) nseg = v;
-    }
-    if (nseg > n_scans) nseg = (int)n_scans;
-    // A piece must end on a 32-byte sector boundary (an even point offset): the kernel reads scans
-    // through L1, and a sector that straddled two pieces could be cached while its second half had
-    // not arrived yet.  Boundaries on a 128-byte line (offset % 8 == 0) are preferred when one is near.
+    int nseg = 0;
     int64_t seg_end[kMaxSegments];                            // exclusive scan id
     {
-        int64_t s = 0;
-        int made = 0;
-        for (int k = 0; k < nseg - 1; ++k) {
-            const int64_t want = total * (k + 1) / nseg;
-            while (s < n_scans && h_offsets[s] < want) ++s;
-            int64_t pick = -1;
-            for (int64_t c = s; c < n_scans && c < s + 64; ++c) {
-                if (h_offsets[c] % 8 == 0) { pick = c; break; }
-                if (pick < 0 && h_offsets[c] % 2 == 0) pick = c;
-            }
-            if (pick <= 0 || pick >= n_scans || (made > 0 && pick <= seg_end[made - 1])) continue;   // merge with the next piece
-            seg_end[made++] = pick;
-            s = pick;
-        }
-        seg_end[made++] = n_scans;
-        nseg = made;
+        int want = 0;
+        if (const char *t = getenv("ICPB_SEGMENTS")) want = atoi(t);      // tuning experiments only
+        if ((rc = icpb_plan_upload(h_offsets, n_scans, want, seg_end, &nseg))) return rc;
     }
     // pinned staging, 8-byte members first:  up = [init | pairs | seg | order],  down = [T | err | passes]
     const size_t nbI = sizeof(double) * 6 * (size_t)B, nbE = sizeof(double) * (size_t)B, nb4 = sizeof(int32_t) * (size_t)B;

@@ -128,6 +128,13 @@ int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
                     const int32_t *h_pairs, const double *h_init, int64_t B, const icpb_params *p,
                     double *h_T, double *h_err, int32_t *h_passes);
 
+/* How icpb_align_host cuts the scan table into upload pieces (pure host logic, no CUDA call; exposed
+ * for tests): piece k covers scans [piece_end[k-1], piece_end[k]); piece_end has room for 64 entries;
+ * pieces_wanted = 0 picks ~4 MB pieces, at most 16.  Every piece ends on an even point offset (a
+ * 32-byte sector of the fp64 table), so no cached sector can mix landed and pending bytes. */
+int icpb_plan_upload(const int64_t *h_offsets, int64_t n_scans, int32_t pieces_wanted,
+                     int64_t *piece_end, int32_t *n_pieces);
+
 /* The same with the transforms in the caller's own layout: init_ld / T_ld = 9 reads and writes the
  * reference's full 3x3 row-major matrices (what scripts/main.py:244 passes and src/icp.py:97
  * returns; the bottom row is checked to be [0, 0, 1] on the way in and written on the way out),

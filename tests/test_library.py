@@ -117,3 +117,33 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
     assert "workload" in d["config"]
+
+
+def test_upload_plan_pieces_end_on_sector_boundaries():
+    """icpb_plan_upload (the host logic that cuts the scan table for the streaming upload): pieces
+    are contiguous, cover every scan, and every interior boundary sits on an even point offset (a
+    32-byte sector of the fp64 table) -- on a 128-byte line when one lies within reach."""
+    from icp_slam_b200 import _lib
+    L = ctypes.CDLL(_lib.build())
+    L.icpb_plan_upload.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        n = int(rng.integers(1, 6000))
+        lens = rng.integers(1, 1200, size=n) if trial % 3 else rng.integers(1, 4, size=n) * 2 + 1   # all-odd lengths too
+        off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        want = int(rng.integers(0, 40))
+        ends = np.zeros(64, dtype=np.int64)
+        k = ctypes.c_int32()
+        rc = L.icpb_plan_upload(off.ctypes.data, n, want, ends.ctypes.data, ctypes.byref(k))
+        assert rc == 0 and 1 <= k.value <= 64
+        e = ends[:k.value]
+        assert e[-1] == n and np.all(np.diff(e) > 0) and e[0] >= 1
+        assert np.all(off[e[:-1]] % 2 == 0)                      # interior boundaries: even point offsets
+        if want == 0:
+            assert k.value <= 16
+    # a table of 5,000 x 1,024-point scans: 16 pieces, all on 128-byte lines
+    off = (np.arange(5001) * 1024).astype(np.int64)
+    ends = np.zeros(64, dtype=np.int64); k = ctypes.c_int32()
+    assert L.icpb_plan_upload(off.ctypes.data, 5000, 0, ends.ctypes.data, ctypes.byref(k)) == 0
+    assert k.value == 16 and np.all(off[ends[:15]] % 8 == 0)
+    assert L.icpb_plan_upload(None, 5000, 0, ends.ctypes.data, ctypes.byref(k)) != 0
