@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 4,999-pair chain, from the
 # committed `ncu --set full` capture (profiles/r01m_align_ncu_full_summary.csv); None until measured
 TRAFFIC_NCU = 85.1e6   # 81.1 MB read (= one pass over the 81 MB scan table) + 4.0 MB written
+WARP_INSTR_NCU = 1405949366.0   # smsp__inst_executed.sum of the same launch (same capture)
 METRIC = "icp_scan_pair_alignments_per_sec"
 UNIT = "pairs/s"
 SEED = 467002
@@ -450,6 +451,13 @@ def main():
             "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kern_s * 1e-9,
                          "peak_gbs": hbm_peak, "frac": alg_bytes / kern_s * 1e-9 / hbm_peak, "peak_source": peak_src},
         }
+        if args.workload == "chain" and args.scans == 5000 and args.beams == 1024:
+            # what actually bounds the pruned kernel: warp-instruction issue slots (4 schedulers per SM,
+            # one instruction per cycle each); the instruction count is the ncu figure of this launch
+            roofline["issue_view"] = {
+                "warp_instructions_per_launch": WARP_INSTR_NCU,
+                "frac_of_issue_peak": WARP_INSTR_NCU / (kern_s * sm_count * 4 * sm_max_mhz * 1e6),
+                "source": "smsp__inst_executed.sum, profiles/r01m_align_ncu_full_summary.csv"}
         cpu = None
         if world == 1 and not args.no_cpu:
             if _ALL_CPUS:
