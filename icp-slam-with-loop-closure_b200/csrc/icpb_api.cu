@@ -166,10 +166,13 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     if (threads < 32) threads = 32;
     c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
     c->nchunk_cap = (int)nchunk; c->ntile_cap = (int)ntile;
-    // Latency mode: with fewer problems than SMs and more tiles than one CTA has warps, spread each
+    // Latency mode: with fewer problems than SMs and more than two tiles per warp of a CTA, spread each
     // problem over a thread-block cluster (a power of two, at most 8 CTAs) so every tile gets a warp.
+    // 1,024-point scans (16 tiles, two per warp) do not qualify: the per-pass cluster barrier and the
+    // fold over distributed shared memory cost more than the second tile (40 pairs: 0.41 ms in single
+    // CTAs, 0.61 ms in clusters of two; tools/midsize_probe.py); 4,096-point pairs gain 1.8x.
     c->cluster = 1;
-    if (fn == pick_kernel(nullptr) && B * 2 <= h->sm_count && nwork > 8) {
+    if (fn == pick_kernel(nullptr) && B * 2 <= h->sm_count && nwork > 16) {
         int cl = 2;
         while (cl < 8 && (int64_t)cl * 8 < nwork) cl *= 2;
         while (cl > 1 && B * cl > h->sm_count) cl /= 2;
