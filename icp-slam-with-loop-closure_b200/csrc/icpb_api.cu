@@ -537,6 +537,7 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     if (rc) return rc;
     if (p->pair_mode != 0 || p->hist_cap > 0 || p->corr_stride > 0)
         return fail(ICPB_EINVAL, "icpb_align_host: explicit pairs, no history/correspondences (use upload + run)%s");
+    if (B >= (int64_t(1) << 31)) return fail(ICPB_EINVAL, "icpb_align_host: at most 2^31 - 1 pairs per call%s");
     int64_t longest = 0;
     if ((rc = validate_offsets(h_offsets, n_scans, &longest))) return rc;
     if (B > 0 && (!h_pairs || !h_T || !h_err || !h_passes)) return fail(ICPB_EINVAL, "null pointer%s");
