@@ -21,7 +21,8 @@ EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destr
            "icpb_count_work", "icpb_read_work", "icpb_align_host", "icpb_align_host_ld", "icpb_plan_upload", "icpb_fit_pairs_host",
            "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
            "icpb_run_device_gather", "icpb_pose_graph_sgd", "icpb_occupancy_grid_bounds",
-           "icpb_occupancy_grid_update"]
+           "icpb_occupancy_grid_update", "icpb_run_device_ex", "icpb_align_host_ex", "icpb_align_host_scans",
+           "icpb_set_tuning", "icpb_scan_count"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -30,6 +31,15 @@ class IcpbParams(ctypes.Structure):
                 ("hist_cap", ctypes.c_int32), ("corr_stride", ctypes.c_int32),
                 ("pair_mode", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("k_first", ctypes.c_int64), ("k_block", ctypes.c_int64), ("k_stride", ctypes.c_int64)]
+
+
+class IcpbEpilogue(ctypes.Structure):
+    """icpb_epilogue (include/icpb.h): fused all-gather and acceptance/compaction of the records."""
+    _fields_ = [("d_peer_ptrs", ctypes.c_void_p), ("n_peers", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("row0", ctypes.c_int64), ("row_block", ctypes.c_int64), ("row_stride", ctypes.c_int64),
+                ("accept_thresh", ctypes.c_double), ("d_accept_rec", ctypes.c_void_p),
+                ("d_accept_count", ctypes.c_void_p), ("d_accept_peer_ptrs", ctypes.c_void_p),
+                ("d_accept_count_peer_ptrs", ctypes.c_void_p), ("accept_cap", ctypes.c_int64)]
 
 
 class IcpbKernelInfo(ctypes.Structure):
@@ -52,6 +62,42 @@ def sources():
                                               os.path.join(c, "icpb_sgd.cuh"),
                                               os.path.join(c, "icpb_grid.cuh"),
                                               os.path.join(_ROOT, "include", "icpb.h")]
+
+
+PYHELPER_SRC = os.path.join(_HERE, "csrc", "icpb_pyhelper.c")
+PYHELPER_SO = os.path.join(_HERE, "_icpb_pyhelper.so")
+
+
+def build_pyhelper(force: bool = False) -> str:
+    """gcc -> _icpb_pyhelper.so: list of numpy arrays -> pointer / length arrays (buffer protocol)."""
+    import sysconfig
+    if not force and os.path.exists(PYHELPER_SO) and os.path.getmtime(PYHELPER_SO) >= os.path.getmtime(PYHELPER_SRC):
+        return PYHELPER_SO
+    import fcntl
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        tmp = f"{PYHELPER_SO}.{os.getpid()}.tmp"
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"],
+                               "-o", tmp, PYHELPER_SRC])
+        os.replace(tmp, PYHELPER_SO)
+    return PYHELPER_SO
+
+
+_pyhelper = None
+
+
+def pyhelper():
+    """The buffer-protocol helper, or None when it cannot be built (callers then use a Python loop)."""
+    global _pyhelper
+    if _pyhelper is None:
+        try:
+            L = ctypes.PyDLL(build_pyhelper())
+            L.icpb_py_scan_ptrs.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong]
+            L.icpb_py_scan_ptrs.restype = ctypes.c_longlong
+            _pyhelper = L
+        except (OSError, subprocess.CalledProcessError):
+            _pyhelper = False
+    return _pyhelper or None
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -108,6 +154,13 @@ def lib() -> ctypes.CDLL:
     L.icpb_run_device.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p, vp]
     L.icpb_run_device_gather.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, vp,
                                          ctypes.c_int32, i64, vp]
+    L.icpb_run_device_ex.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p,
+                                     ctypes.POINTER(IcpbEpilogue), vp]
+    L.icpb_align_host_ex.argtypes = [vp, dp, vp, i64, i32p, dp, ctypes.c_int32, i64, ctypes.POINTER(IcpbParams),
+                                     dp, ctypes.c_int32, dp, i32p, ctypes.POINTER(IcpbEpilogue)]
+    L.icpb_align_host_scans.argtypes = [vp, vp, vp, i64, i32p, dp, ctypes.c_int32, i64, ctypes.POINTER(IcpbParams),
+                                        dp, ctypes.c_int32, dp, i32p, ctypes.POINTER(IcpbEpilogue)]
+    L.icpb_set_tuning.argtypes = [vp, ctypes.c_char_p, i64]
     L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_align_host.argtypes = [vp, dp, vp, i64, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p]
     L.icpb_align_host_ld.argtypes = [vp, dp, vp, i64, i32p, dp, ctypes.c_int32, i64, ctypes.POINTER(IcpbParams),
@@ -127,6 +180,8 @@ def lib() -> ctypes.CDLL:
     L.icpb_get_kernel_info.argtypes = [vp, i64, ctypes.POINTER(IcpbKernelInfo)]
     L.icpb_launch_count.argtypes = [vp]
     L.icpb_launch_count.restype = ctypes.c_int64
+    L.icpb_scan_count.argtypes = [vp]
+    L.icpb_scan_count.restype = ctypes.c_int64
     L.icpb_last_error.restype = ctypes.c_char_p
     L.icpb_count_work.argtypes = [vp, ctypes.c_int]
     L.icpb_read_work.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]

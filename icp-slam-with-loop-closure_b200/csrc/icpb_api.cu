@@ -8,7 +8,12 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <atomic>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <time.h>
+#include <sched.h>
 
 #include "icpb.h"
 #include "icpb_kernels.cuh"
@@ -34,6 +39,30 @@ int fail(int code, const char *fmt, const char *detail = "")
             return (int)e_;                                                               \
         }                                                                                 \
     } while (0)
+
+// Every entry point runs on the handle's device and puts the caller's current device back on the
+// way out (a torch process with several devices must not find its current device changed).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) {
+            const cudaError_t e = cudaSetDevice(device);
+            if (e != cudaSuccess) {
+                snprintf(g_err, sizeof g_err, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+                ok = false;
+            }
+        } else {
+            prev = -1;                                        // nothing to restore
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h)                                      \
+    DeviceGuard guard_((h)->device);                      \
+    if (!guard_.ok) return (int)cudaErrorInvalidDevice
 
 #ifndef ICPB_R
 #define ICPB_R 2
@@ -107,6 +136,104 @@ kernel_fn cluster_kernel() { return icpb::icp_align_kernel<kPointsPerThread, tru
 
 }  // namespace
 
+namespace {
+
+// A few host threads that copy scans from the caller's (pageable, scattered) arrays into the pinned
+// staging table, one job = a run of consecutive scans.  Jobs are handed out in table order, so the
+// first upload piece is complete first; `done[k]` counts the finished jobs of piece k and the
+// dispatching thread enqueues the piece's copy as soon as it is full.
+struct PackJob {
+    const double *const *scan_xy;       // n_scans pointers to (m_i, 2) float64 rows
+    const int64_t *offsets;             // CSR offsets of the packed table
+    double *dst;                        // pinned staging
+    const int64_t *job_first, *job_last;  // scans [first, last) of job j
+    const int32_t *job_piece;           // upload piece of job j
+    int64_t n_jobs;
+    std::atomic<int64_t> next{0};
+    std::atomic<int32_t> *done;         // per piece
+    std::atomic<uint64_t> bad{0};       // non-finite coordinate seen
+};
+
+static void pack_run(PackJob *job)
+{
+    for (;;) {
+        const int64_t j = job->next.fetch_add(1, std::memory_order_relaxed);
+        if (j >= job->n_jobs) break;
+        uint64_t bad = 0;
+        for (int64_t s = job->job_first[j]; s < job->job_last[j]; ++s) {
+            const int64_t o = job->offsets[s], m = job->offsets[s + 1] - o;
+            const double *src = job->scan_xy[s];
+            double *d = job->dst + 2 * o;
+            memcpy(d, src, sizeof(double) * 2 * (size_t)m);
+            // finiteness check on the copy (cache-resident): all-ones exponent = inf or NaN
+            const uint64_t *u = (const uint64_t *)d;
+            for (int64_t k = 0; k < 2 * m; ++k)
+                bad |= (uint64_t)((u[k] & 0x7ff0000000000000ULL) == 0x7ff0000000000000ULL);
+        }
+        if (bad) job->bad.fetch_or(1, std::memory_order_relaxed);
+        job->done[job->job_piece[j]].fetch_add(1, std::memory_order_release);
+    }
+}
+
+struct PackPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    PackJob *job = nullptr;
+    uint64_t generation = 0;
+    int running = 0;
+    bool stop = false;
+
+    explicit PackPool(int n)
+    {
+        for (int t = 0; t < n; ++t)
+            workers.emplace_back([this] {
+                uint64_t seen = 0;
+                for (;;) {
+                    PackJob *j;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        j = job;
+                    }
+                    pack_run(j);
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        --running;
+                    }
+                    cv.notify_all();
+                }
+            });
+    }
+    void start(PackJob *j)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = j; ++generation; running = (int)workers.size();
+        }
+        cv.notify_all();
+    }
+    void finish()                                       // the caller packs too, then waits for the workers
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return running == 0; });
+        job = nullptr;
+    }
+    ~PackPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &w : workers) w.join();
+    }
+};
+
+}  // namespace
+
 struct icpb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -134,7 +261,13 @@ struct icpb_ctx {
     PinnedBuf stage;                                // pinned staging of the small per-call arrays
     DevBuf s_sgd;                                   // pose-graph SGD: poses, edges, transforms, scratch
     DevBuf s_grid;                                  // occupancy grid: poses, per-cell words, the grid
+    DevBuf s_accept;                                // acceptance epilogue: [appended, CTAs left] counters
+    PinnedBuf stage_xy;                             // pinned copy of a scan table packed from a list of arrays
+    PackPool *pool = nullptr;                       // host threads that pack scans into stage_xy
     int max_smem_set = 0;
+    // tuning / test hooks (icpb_set_tuning); 0 or -1 = the library's own choice
+    int tune_threads = 0, tune_cluster = -1, tune_segments = 0, tune_sgd_cluster = 0, tune_pack_threads = 0;
+    bool tune_flag_copy = false, tune_drop_counter = false, tune_trace = false;
 };
 
 namespace {
@@ -142,12 +275,14 @@ namespace {
 int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn, int R = kPointsPerThread)
 {
     if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
-    const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk;
+    // targets padded to whole chunks, plus one all-padding chunk that idle pruning groups sweep
+    const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk + icpb::kChunk;
     const int64_t n1c = (longest + 3) & ~int64_t(3);
     const int64_t nchunk = n2pad / icpb::kChunk;
     const int64_t ntile = (longest + 63) / 64;              // 64-point reduction tiles (independent of R)
     const int64_t nwork = (ntile + R / 2 - 1) / (R / 2);    // warp work items of 32*R points
-    const int64_t smem = 8 * n2pad + 16 * nchunk + 4 * n1c + 8 * (2 * ntile * icpb::kNumSums + icpb::kMaxWarps * 6);
+    const int64_t smem = 8 * n2pad + 16 * nchunk + 16 * (icpb::kGroups + 1) * ntile + 4 * n1c +
+                         8 * (2 * ntile * icpb::kNumSums + icpb::kMaxWarps * icpb::kTw + 2);
     if (smem > kMaxSmem) {
         snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
                  (long long)longest, (long long)smem, kMaxSmem);
@@ -158,10 +293,8 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     // barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
     // problems per resident CTA (tail) or a single pair (latency).
     int max_threads = (B >= 2048 && R < 4) ? 128 : 256;
-    if (const char *t = getenv("ICPB_THREADS")) {         // tuning experiments only
-        const int v = atoi(t);
-        if (v >= 32 && v <= 256 && v % 32 == 0) max_threads = v;
-    }
+    if (h->tune_threads >= 32 && h->tune_threads <= 256 && h->tune_threads % 32 == 0)
+        max_threads = h->tune_threads;                    // icpb_set_tuning("threads")
     if (threads > max_threads) threads = max_threads;
     if (threads < 32) threads = 32;
     c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
@@ -178,8 +311,8 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
         while (cl > 1 && B * cl > h->sm_count) cl /= 2;
         c->cluster = cl;
     }
-    if (const char *t = getenv("ICPB_CLUSTER")) {         // tuning / tests: force a cluster size (0 = never)
-        const int v = atoi(t);
+    if (h->tune_cluster >= 0) {                           // icpb_set_tuning("cluster"): force a size (0 = never)
+        const int v = h->tune_cluster;
         if (v == 0 || v == 1) c->cluster = 1;
         else if ((v == 2 || v == 4 || v == 8) && fn == pick_kernel(nullptr)) c->cluster = v;
     }
@@ -210,12 +343,31 @@ int check_params(const icpb_params *p, int64_t B)
     return 0;
 }
 
+int check_epilogue(const icpb_epilogue *ep, const icpb_params *p)
+{
+    if (!ep) return 0;
+    const bool gather = ep->d_peer_ptrs != nullptr;
+    const bool accept = ep->d_accept_rec != nullptr || ep->d_accept_peer_ptrs != nullptr;
+    if ((gather || ep->d_accept_peer_ptrs) && (ep->n_peers < 1 || ep->n_peers > 64))
+        return fail(ICPB_EINVAL, "epilogue: 1..64 peer buffers expected%s");
+    if (ep->row0 < 0 || ep->row_stride < 0) return fail(ICPB_EINVAL, "epilogue: negative row0 / row_stride%s");
+    if (accept) {
+        if (ep->accept_cap < 1) return fail(ICPB_EINVAL, "epilogue: accept_cap must be >= 1%s");
+        if (isnan(ep->accept_thresh)) return fail(ICPB_EINVAL, "epilogue: NaN accept_thresh%s");
+        if (ep->d_accept_peer_ptrs && (!ep->d_accept_count_peer_ptrs || ep->rank < 0 || ep->rank >= ep->n_peers))
+            return fail(ICPB_EINVAL, "epilogue: peer acceptance needs the peers' count arrays and a rank in range%s");
+        if (!ep->d_accept_peer_ptrs && !ep->d_accept_count) return fail(ICPB_EINVAL, "epilogue: d_accept_count is null%s");
+    }
+    (void)p;
+    return 0;
+}
+
 int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scans, int64_t longest,
            const int32_t *d_pairs, const double *d_init, int64_t B, const icpb_params *p,
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
            cudaStream_t stream, int64_t B_total = 0, const int32_t *d_seg_of_pair = nullptr,
-           const int32_t *d_arrived = nullptr, double *const *d_peers = nullptr, int n_peers = 0,
-           int64_t rec_row0 = 0, const int32_t *d_order = nullptr, int32_t *d_upload_timeout = nullptr)
+           const int32_t *d_arrived = nullptr, const icpb_epilogue *ep = nullptr,
+           const int32_t *d_order = nullptr, int32_t *d_upload_timeout = nullptr)
 {
     if (B == 0) return 0;
     LaunchCfg cfg;
@@ -232,7 +384,25 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
     a.executed = h->executed;
     a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived; a.order = d_order; a.upload_timeout = d_upload_timeout;
-    a.peers = d_peers; a.n_peers = n_peers; a.rec_row0 = rec_row0;
+    a.peers = nullptr; a.n_peers = 0; a.rec_row0 = 0; a.rec_block = B > 0 ? B : 1; a.rec_stride = 0;
+    a.accept_thresh = 0.0; a.accept_rec = nullptr; a.accept_peers = nullptr; a.accept_ctr = nullptr;
+    a.accept_count_out = nullptr; a.accept_count_peers = nullptr; a.accept_cap = 0; a.accept_rank = 0;
+    if (ep) {
+        a.peers = (double *const *)ep->d_peer_ptrs; a.n_peers = ep->n_peers;
+        a.rec_row0 = ep->row0; a.rec_stride = ep->row_stride;
+        if (ep->row_block > 0) a.rec_block = ep->row_block;
+        if (ep->d_accept_rec || ep->d_accept_peer_ptrs) {
+            int rc2;
+            if ((rc2 = h->s_accept.reserve(2 * sizeof(unsigned long long)))) return rc2;
+            a.accept_thresh = ep->accept_thresh; a.accept_cap = ep->accept_cap; a.accept_rank = ep->rank;
+            a.accept_rec = ep->d_accept_peer_ptrs ? nullptr : ep->d_accept_rec;
+            a.accept_peers = (double *const *)ep->d_accept_peer_ptrs;
+            a.accept_count_peers = (long long *const *)ep->d_accept_count_peer_ptrs;
+            a.accept_count_out = (long long *)ep->d_accept_count;
+            a.accept_ctr = (unsigned long long *)h->s_accept.p;
+            CU(cudaMemsetAsync(a.accept_ctr, 0, 2 * sizeof(unsigned long long), stream));
+        }
+    }
     CU(cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream));
     int64_t grid = (int64_t)cfg.ctas_per_sm * h->sm_count;
     if (grid > B) grid = B;
@@ -241,11 +411,16 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)cfg.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        int64_t clusters = grid / cfg.cluster;              // resident CTAs -> clusters
-        if (clusters < 1) clusters = 1;
-        if (clusters > B) clusters = B;
-        lc.gridDim = dim3((unsigned)(clusters * cfg.cluster)); lc.blockDim = dim3((unsigned)cfg.threads);
+        lc.blockDim = dim3((unsigned)cfg.threads);
         lc.dynamicSmemBytes = (size_t)cfg.smem; lc.stream = stream; lc.attrs = attr; lc.numAttrs = 1;
+        // one cluster per problem, as many as the device can co-schedule (the occupancy query needs a
+        // grid that is a multiple of the cluster size; it answers in clusters)
+        lc.gridDim = dim3((unsigned)cfg.cluster);
+        int max_clusters = 0;
+        CU(cudaOccupancyMaxActiveClusters(&max_clusters, cluster_kernel(), &lc));
+        int64_t clusters = max_clusters > 0 ? max_clusters : 1;
+        if (clusters > B) clusters = B;
+        lc.gridDim = dim3((unsigned)(clusters * cfg.cluster));
         CU(cudaLaunchKernelEx(&lc, cluster_kernel(), a));
     } else {
         fn<<<(unsigned)grid, cfg.threads, cfg.smem, stream>>>(a);
@@ -279,7 +454,8 @@ int icpb_create(int device, icpb_handle *out)
     int count = 0;
     CU(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(ICPB_EINVAL, "no such CUDA device%s");
-    CU(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    if (!guard_.ok) return (int)cudaErrorInvalidDevice;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -300,7 +476,7 @@ int icpb_create(int device, icpb_handle *out)
     if (e == cudaSuccess) e = cudaMalloc(&h->arrived_dev, sizeof(int32_t));
     if (e == cudaSuccess) e = cudaHostAlloc(&h->seg_vals_pinned, sizeof(int32_t) * (kMaxSegments + 1), cudaHostAllocDefault);
     if (e == cudaSuccess) for (int k = 0; k <= kMaxSegments; ++k) h->seg_vals_pinned[k] = k;
-    if (e == cudaSuccess && !getenv("ICPB_FLAG_COPY")) {
+    if (e == cudaSuccess) {
         void *fp = nullptr;
         cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fp, cudaEnableDefault, &qr) == cudaSuccess &&
@@ -310,19 +486,39 @@ int icpb_create(int device, icpb_handle *out)
             cudaGetLastError();
     }
     if (e != cudaSuccess) {
+        icpb_destroy(h);                                      // frees whatever was created so far
         snprintf(g_err, sizeof g_err, "icpb_create: %s", cudaGetErrorString(e));
-        if (h->queue) cudaFree(h->queue);
-        delete h;
         return (int)e;
     }
     *out = h;
     return 0;
 }
 
+int icpb_set_tuning(icpb_handle h, const char *key, int64_t value)
+{
+    if (!h || !key) return fail(ICPB_EINVAL, "icpb_set_tuning: bad argument%s");
+    const int v = (int)value;
+    if (!strcmp(key, "threads")) h->tune_threads = v;
+    else if (!strcmp(key, "cluster")) h->tune_cluster = v;
+    else if (!strcmp(key, "segments")) h->tune_segments = v;
+    else if (!strcmp(key, "sgd_cluster")) h->tune_sgd_cluster = v;
+    else if (!strcmp(key, "pack_threads")) {
+        if (h->pool && (int)h->pool->workers.size() != v - 1) { delete h->pool; h->pool = nullptr; }
+        h->tune_pack_threads = v;
+    }
+    else if (!strcmp(key, "flag_copy")) h->tune_flag_copy = v != 0;
+    else if (!strcmp(key, "drop_counter")) h->tune_drop_counter = v != 0;
+    else if (!strcmp(key, "trace")) h->tune_trace = v != 0;
+    else return fail(ICPB_EINVAL, "icpb_set_tuning: unknown key %s", key);
+    return 0;
+}
+
 int icpb_destroy(icpb_handle h)
 {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
+    delete h->pool;
+    h->pool = nullptr;
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     for (int k = 0; k < 2; ++k) if (h->cstream[k]) { cudaStreamSynchronize(h->cstream[k]); cudaStreamDestroy(h->cstream[k]); }
     for (int k = 0; k < 16; ++k) if (h->seg_ev[k]) cudaEventDestroy(h->seg_ev[k]);
@@ -330,6 +526,7 @@ int icpb_destroy(icpb_handle h)
     if (h->arrived_dev) cudaFree(h->arrived_dev);
     if (h->seg_vals_pinned) cudaFreeHost(h->seg_vals_pinned);
     h->s_seg.release(); h->stage.release(); h->s_sgd.release(); h->s_grid.release();
+    h->s_accept.release(); h->stage_xy.release();
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -358,7 +555,7 @@ int icpb_upload_scans(icpb_handle h, const double *h_xy, const int64_t *h_offset
     int64_t longest = 0;
     int rc = validate_offsets(h_offsets, n_scans, &longest);
     if (rc) return rc;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t nb_xy = sizeof(double) * 2 * (size_t)h_offsets[n_scans];
     const size_t nb_off = sizeof(int64_t) * (size_t)(n_scans + 1);
     if ((rc = h->own_xy.reserve(nb_xy))) return rc;
@@ -396,28 +593,37 @@ int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init,
     if (p->corr_stride > 0 && !d_corr) return fail(ICPB_EINVAL, "corr_stride > 0 but corr is null%s");
     if (p->corr_stride > 0 && p->corr_stride < h->longest)
         return fail(ICPB_EINVAL, "corr_stride is smaller than the longest scan%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     return launch(h, h->xy, h->offsets, h->n_scans, h->longest, d_pairs, d_init, B, p,
                   d_T, d_err, d_passes, d_hist, d_corr, (cudaStream_t)stream);
+}
+
+int icpb_run_device_ex(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
+                       const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
+                       const icpb_epilogue *ep, void *stream)
+{
+    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if ((rc = check_epilogue(ep, p))) return rc;
+    if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
+    if (B > 0 && (!d_T || !d_err || !d_passes)) return fail(ICPB_EINVAL, "output pointer is null%s");
+    if (B > 0 && p->pair_mode == 0 && !d_pairs) return fail(ICPB_EINVAL, "pairs is null with pair_mode 0%s");
+    if (p->hist_cap > 0 || p->corr_stride > 0) return fail(ICPB_EINVAL, "icpb_run_device_ex: no history/correspondences%s");
+    ON_DEVICE(h);
+    return launch(h, h->xy, h->offsets, h->n_scans, h->longest, d_pairs, d_init, B, p, d_T, d_err, d_passes,
+                  nullptr, nullptr, (cudaStream_t)stream, 0, nullptr, nullptr, ep);
 }
 
 int icpb_run_device_gather(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
                            const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
                            const uint64_t *d_peer_ptrs, int32_t n_peers, int64_t row0, void *stream)
 {
-    if (!h) return fail(ICPB_EINVAL, "handle is null%s");
-    int rc = check_params(p, B);
-    if (rc) return rc;
-    if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
-    if (B > 0 && (!d_T || !d_err || !d_passes)) return fail(ICPB_EINVAL, "output pointer is null%s");
-    if (B > 0 && p->pair_mode == 0 && !d_pairs) return fail(ICPB_EINVAL, "pairs is null with pair_mode 0%s");
-    if (!d_peer_ptrs || n_peers < 1 || n_peers > 8 || row0 < 0)
-        return fail(ICPB_EINVAL, "icpb_run_device_gather: 1..8 peer buffers expected%s");
-    if (p->hist_cap > 0 || p->corr_stride > 0) return fail(ICPB_EINVAL, "icpb_run_device_gather: no history/correspondences%s");
-    CU(cudaSetDevice(h->device));
-    return launch(h, h->xy, h->offsets, h->n_scans, h->longest, d_pairs, d_init, B, p, d_T, d_err, d_passes,
-                  nullptr, nullptr, (cudaStream_t)stream, 0, nullptr, nullptr,
-                  (double *const *)d_peer_ptrs, n_peers, row0);
+    if (!d_peer_ptrs) return fail(ICPB_EINVAL, "icpb_run_device_gather: peer buffers expected%s");
+    icpb_epilogue ep;
+    memset(&ep, 0, sizeof ep);
+    ep.d_peer_ptrs = d_peer_ptrs; ep.n_peers = n_peers; ep.row0 = row0;
+    return icpb_run_device_ex(h, d_pairs, d_init, B, p, d_T, d_err, d_passes, &ep, stream);
 }
 
 static int run_host_common(icpb_handle h, const double *xy, const int64_t *offsets, int64_t n_scans,
@@ -477,7 +683,7 @@ int icpb_run_host(icpb_handle h, const int32_t *h_pairs, const double *h_init, i
         for (int64_t b = 0; b < 2 * B; ++b)
             if (h_pairs[b] < 0 || h_pairs[b] >= h->n_scans) return fail(ICPB_EINVAL, "pair index out of range%s");
     }
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     return run_host_common(h, h->xy, h->offsets, h->n_scans, h->longest, h_pairs, h_init, B, p,
                            h_T, h_err, h_passes, h_hist, h_corr);
 }
@@ -524,23 +730,57 @@ int icpb_plan_upload(const int64_t *h_offsets, int64_t n_scans, int32_t pieces_w
     return 0;
 }
 
-int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
-                       const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
-                       const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes)
+namespace {
+
+// Where icpb_align_host*'s scan table comes from: one packed (sum m_i, 2) array with its offsets, or the
+// reference's own `lidar_points` form -- a list of separate (m_i, 2) arrays in pageable memory.
+struct TableSrc {
+    const double *xy = nullptr;                 // packed form
+    const int64_t *offsets = nullptr;           // n_scans + 1 (computed from the lengths for the list form)
+    const double *const *scan_xy = nullptr;     // list form
+};
+
+// Everything that was enqueued is drained before an error is reported, and the handle is left without
+// a table: its buffer may hold a mixture of the old and the new scans.
+int align_abort(icpb_ctx *h, int rc)
 {
-    if (!h || !h_xy || !h_offsets || n_scans <= 0) return fail(ICPB_EINVAL, "icpb_align_host: bad argument%s");
-    if ((init_ld != 6 && init_ld != 9) || (T_ld != 6 && T_ld != 9))
-        return fail(ICPB_EINVAL, "icpb_align_host: init_ld / T_ld must be 6 (2x3 rows) or 9 (3x3)%s");
-    static const bool trace = getenv("ICPB_TRACE") != nullptr;
+    char keep[sizeof g_err];
+    memcpy(keep, g_err, sizeof keep);
+    cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->cstream[0]); cudaStreamSynchronize(h->cstream[1]);
+    cudaGetLastError();
+    memcpy(g_err, keep, sizeof keep);
+    h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
+    return rc;
+}
+#define CUA(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            snprintf(g_err, sizeof g_err, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            return align_abort(h, (int)e_);                                               \
+        }                                                                                 \
+    } while (0)
+
+int host_threads_available()
+{
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return n;
+    }
+    const unsigned n = std::thread::hardware_concurrency();
+    return n > 0 ? (int)n : 1;
+}
+
+int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t longest,
+               const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+               const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
+               const icpb_epilogue *ep)
+{
+    const bool trace = h->tune_trace;
     const double t_entry = trace ? now_us() : 0.0;
-    int rc = check_params(p, B);
-    if (rc) return rc;
-    if (p->pair_mode != 0 || p->hist_cap > 0 || p->corr_stride > 0)
-        return fail(ICPB_EINVAL, "icpb_align_host: explicit pairs, no history/correspondences (use upload + run)%s");
-    if (B >= (int64_t(1) << 31)) return fail(ICPB_EINVAL, "icpb_align_host: at most 2^31 - 1 pairs per call%s");
-    int64_t longest = 0;
-    if ((rc = validate_offsets(h_offsets, n_scans, &longest))) return rc;
-    if (B > 0 && (!h_pairs || !h_T || !h_err || !h_passes)) return fail(ICPB_EINVAL, "null pointer%s");
+    const int64_t *h_offsets = src.offsets;
+    int rc;
     {
         int32_t lo = 0, hi = 0;                               // branch-free range check
         for (int64_t b = 0; b < 2 * B; ++b) { lo = h_pairs[b] < lo ? h_pairs[b] : lo; hi = h_pairs[b] > hi ? h_pairs[b] : hi; }
@@ -560,32 +800,23 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
         }
         if (bad) return fail(ICPB_EINVAL, "transform holds non-finite values%s");
     }
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t nb_xy = sizeof(double) * 2 * (size_t)h_offsets[n_scans];
     const size_t nb_off = sizeof(int64_t) * (size_t)(n_scans + 1);
     if ((rc = h->own_xy.reserve(nb_xy))) return rc;
     if ((rc = h->own_off.reserve(nb_off))) return rc;
-    h->xy = (const double *)h->own_xy.p; h->offsets = (const int64_t *)h->own_off.p;
-    h->n_scans = n_scans; h->longest = longest;
-    if (B == 0) {
-        CU(cudaMemcpyAsync(h->own_xy.p, h_xy, nb_xy, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        return 0;
-    }
+    if (src.scan_xy && (rc = h->stage_xy.reserve(nb_xy))) return rc;
     int nseg = 0;
     int64_t seg_end[kMaxSegments];                            // exclusive scan id
-    {
-        int want = 0;
-        if (const char *t = getenv("ICPB_SEGMENTS")) want = atoi(t);      // tuning experiments only
-        if ((rc = icpb_plan_upload(h_offsets, n_scans, want, seg_end, &nseg))) return rc;
-    }
+    if ((rc = icpb_plan_upload(h_offsets, n_scans, B == 0 ? 1 : h->tune_segments, seg_end, &nseg))) return rc;
     // pinned staging, 8-byte members first:  up = [init | pairs | seg | order],  down = [T | err | passes]
     const size_t nbI = sizeof(double) * 6 * (size_t)B, nbE = sizeof(double) * (size_t)B, nb4 = sizeof(int32_t) * (size_t)B;
     const size_t nb_up = nbI + 4 * nb4, nb_down = nbI + nbE + nb4 + sizeof(int32_t);   // + the "upload timed out" word
     if ((rc = h->stage.reserve(nb_up + nb_down))) return rc;
     if ((rc = h->s_init.reserve(nb_up))) return rc;
     if ((rc = h->s_T.reserve(nb_down))) return rc;
+    // ---- from here on the handle's table is being replaced: a failure leaves it without one ----
+    h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
     double *pinit = (double *)h->stage.p;
     int32_t *ppairs = (int32_t *)(pinit + 6 * B), *pseg = ppairs + 2 * B, *porder = pseg + B;
     double *tT = (double *)((char *)h->stage.p + nb_up), *tE = tT + 6 * B;
@@ -594,37 +825,97 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     int32_t *d_pairs = (int32_t *)(d_init + 6 * B), *d_seg = d_pairs + 2 * B, *d_order = d_seg + B;
     double *d_T = (double *)h->s_T.p, *d_err = d_T + 6 * B;
     int32_t *d_passes = (int32_t *)(d_err + B);
+    const double *d_xy = (const double *)h->own_xy.p;
+    const int64_t *d_off = (const int64_t *)h->own_off.p;
+
+    // ---- list form: host threads pack the scans into pinned staging, piece by piece ----
+    PackJob job;
+    std::vector<int64_t> job_first, job_last;
+    std::vector<int32_t> job_piece, jobs_of_piece;
+    std::vector<std::atomic<int32_t>> piece_done(src.scan_xy ? (size_t)nseg : 0);
+    const double *up_xy = src.xy;
+    if (src.scan_xy) {
+        int nthr = h->tune_pack_threads > 0 ? h->tune_pack_threads : host_threads_available();
+        if (nthr > 8) nthr = 8;
+        if (nthr < 1) nthr = 1;
+        if (!h->pool && nthr > 1) h->pool = new (std::nothrow) PackPool(nthr - 1);
+        jobs_of_piece.assign((size_t)nseg, 0);
+        for (int k = 0, s0 = 0; k < nseg; ++k) {              // every piece split into nthr runs of scans
+            const int64_t s1 = seg_end[k], n = s1 - s0;
+            const int parts = (int)(n < nthr ? n : nthr);
+            for (int q = 0; q < parts; ++q) {
+                job_first.push_back(s0 + n * q / parts); job_last.push_back(s0 + n * (q + 1) / parts);
+                job_piece.push_back(k);
+            }
+            jobs_of_piece[(size_t)k] = parts;
+            piece_done[(size_t)k].store(0, std::memory_order_relaxed);
+            s0 = (int)s1;
+        }
+        job.scan_xy = src.scan_xy; job.offsets = h_offsets; job.dst = (double *)h->stage_xy.p;
+        job.job_first = job_first.data(); job.job_last = job_last.data(); job.job_piece = job_piece.data();
+        job.n_jobs = (int64_t)job_first.size(); job.done = piece_done.data();
+        if (h->pool) h->pool->start(&job);
+        up_xy = (const double *)h->stage_xy.p;
+    }
+    // once the pool runs, every exit path must stop it first (the job lives on this stack frame)
+    auto pack_finish = [&]() {
+        if (!src.scan_xy) return;
+        job.next.store(job.n_jobs, std::memory_order_relaxed);   // hand out no more jobs
+        if (h->pool) h->pool->finish();
+    };
+#define CUP(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            snprintf(g_err, sizeof g_err, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            pack_finish();                                                                \
+            return align_abort(h, (int)e_);                                               \
+        }                                                                                 \
+    } while (0)
+
+    cudaStream_t cp = h->stream, cp2 = h->cstream[1], cs = h->cstream[0];
+    if (B == 0) {                                             // upload only
+        if (src.scan_xy) { pack_run(&job); pack_finish(); }
+        if (src.scan_xy && job.bad.load()) return align_abort(h, fail(ICPB_EINVAL, "scan table holds non-finite coordinates%s"));
+        CUA(cudaMemcpyAsync(h->own_xy.p, up_xy, nb_xy, cudaMemcpyHostToDevice, cp));
+        CUA(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
+        CUA(cudaStreamSynchronize(cp));
+        h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
+        return 0;
+    }
     // The first pieces start NOW, before the per-pair staging below: the copy engine works while the
     // host sorts and packs (everything has been validated above; nothing below can fail on user input).
-    cudaStream_t cp = h->stream, cp2 = h->cstream[1], cs = h->cstream[0];
-    const bool drop_counter = getenv("ICPB_TEST_DROP_COUNTER") != nullptr;
     int64_t s_prev = 0;
-    auto enqueue_piece = [&](int k) -> int {
+    auto enqueue_piece = [&](int k) -> cudaError_t {
         const int64_t o0 = h_offsets[s_prev], o1 = h_offsets[seg_end[k]];
+        cudaError_t e = cudaSuccess;
         if (o1 > o0)
-            CU(cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, h_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
-                               cudaMemcpyHostToDevice, cp));
+            e = cudaMemcpyAsync((double *)h->own_xy.p + 2 * o0, up_xy + 2 * o0, sizeof(double) * 2 * (size_t)(o1 - o0),
+                                cudaMemcpyHostToDevice, cp);
         // stream order: the counter changes after the segment it announces has landed
-        if (drop_counter) {
-            // tests only: the kernel must time out and the batch be rerun
-        } else if (!h->write32 || h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0) {
-            CU(cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+        if (e != cudaSuccess || h->tune_drop_counter) {
+            // (drop_counter, tests only: the kernel must time out and the batch be rerun)
+        } else if (h->tune_flag_copy || !h->write32 ||
+                   h->write32(cp, (unsigned long long)(uintptr_t)h->arrived_dev, (unsigned)(k + 1), 0) != 0) {
+            e = cudaMemcpyAsync(h->arrived_dev, h->seg_vals_pinned + (k + 1), sizeof(int32_t), cudaMemcpyHostToDevice, cp);
         }
         s_prev = seg_end[k];
-        return 0;
+        return e;
     };
-    CU(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
-    CU(cudaEventRecord(h->seg_ev[1], cp));                    // the counter is zero before the kernel may start
-    const int n_early = nseg < 4 ? nseg : 4;
-    for (int k = 0; k < n_early; ++k)
-        if ((rc = enqueue_piece(k))) return rc;
+    CUP(cudaMemsetAsync(h->arrived_dev, 0, sizeof(int32_t), cp));
+    CUP(cudaEventRecord(h->seg_ev[1], cp));                   // the counter is zero before the kernel may start
+    int n_sent = 0;
+    if (!src.scan_xy) {
+        const int n_early = nseg < 4 ? nseg : 4;
+        for (; n_sent < n_early; ++n_sent) CUP(enqueue_piece(n_sent));
+    }
     // Queue order: pairs grouped by the segment that completes them; the pairs, initial guesses and
     // results themselves stay in the caller's order.  A batch that already comes in arrival order
     // (the odometry chain does) needs no permutation at all.
     bool in_order = true;
     {
         std::vector<int32_t> seg_of_scan((size_t)n_scans);
-        for (int64_t s = 0, k = 0; s < n_scans; ++s) { while (s >= seg_end[k]) ++k; seg_of_scan[s] = (int32_t)k; }
+        for (int64_t sc = 0, k = 0; sc < n_scans; ++sc) { while (sc >= seg_end[k]) ++k; seg_of_scan[sc] = (int32_t)k; }
         int32_t *seg_of_pair = tP;                            // scratch: the download area is free until the end
         int32_t prev = 0, sorted = 1;
         for (int64_t b = 0; b < B; ++b) {
@@ -657,35 +948,60 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
     }
     const double t_prep = trace ? now_us() : 0.0;
     // the small per-pair block goes up on a second copy stream, beside the pieces already in flight
-    CU(cudaMemsetAsync(d_passes + B, 0, sizeof(int32_t), cp2));
-    CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp2));
+    CUP(cudaMemsetAsync(d_passes + B, 0, sizeof(int32_t), cp2));
+    CUP(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp2));
     const size_t nb_idx = (in_order ? 3 : 4) * nb4;           // pairs, seg (, order)
-    if (h_init) CU(cudaMemcpyAsync(d_init, pinit, nbI + nb_idx, cudaMemcpyHostToDevice, cp2));
-    else        CU(cudaMemcpyAsync(d_pairs, ppairs, nb_idx, cudaMemcpyHostToDevice, cp2));
-    CU(cudaEventRecord(h->seg_ev[0], cp2));
+    if (h_init) CUP(cudaMemcpyAsync(d_init, pinit, nbI + nb_idx, cudaMemcpyHostToDevice, cp2));
+    else        CUP(cudaMemcpyAsync(d_pairs, ppairs, nb_idx, cudaMemcpyHostToDevice, cp2));
+    CUP(cudaEventRecord(h->seg_ev[0], cp2));
     // ONE launch over all pairs, in arrival order; its CTAs wait on the segment counter
-    CU(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
-    CU(cudaStreamWaitEvent(cs, h->seg_ev[1], 0));
-    rc = launch(h, h->xy, h->offsets, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
-                d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, nullptr, 0, 0,
+    CUP(cudaStreamWaitEvent(cs, h->seg_ev[0], 0));
+    CUP(cudaStreamWaitEvent(cs, h->seg_ev[1], 0));
+    rc = launch(h, d_xy, d_off, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
+                d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, ep,
                 in_order ? nullptr : d_order, d_passes + B);
-    if (rc) { cudaStreamSynchronize(cp); cudaStreamSynchronize(cp2); return rc; }
-    for (int k = n_early; k < nseg; ++k)
-        if ((rc = enqueue_piece(k))) { cudaStreamSynchronize(cp); cudaStreamSynchronize(cs); return rc; }
-    CU(cudaEventRecord(h->done_ev[0], cs));
-    CU(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
-    CU(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+    if (rc) { pack_finish(); return align_abort(h, rc); }
+    bool bad_scans = false;
+    for (int k = n_sent; k < nseg; ++k) {
+        if (src.scan_xy) {
+            // this thread packs too while a piece is incomplete (pack_run returns when no job is left)
+            while (piece_done[(size_t)k].load(std::memory_order_acquire) < jobs_of_piece[(size_t)k]) {
+                const int64_t j = job.next.fetch_add(1, std::memory_order_relaxed);
+                if (j < job.n_jobs) {
+                    PackJob one;                              // run exactly job j on this thread
+                    one.scan_xy = job.scan_xy; one.offsets = job.offsets; one.dst = job.dst;
+                    one.job_first = job.job_first + j; one.job_last = job.job_last + j; one.job_piece = job.job_piece + j;
+                    one.n_jobs = 1; one.done = job.done;
+                    pack_run(&one);
+                    if (one.bad.load()) job.bad.fetch_or(1, std::memory_order_relaxed);
+                }
+            }
+            if (job.bad.load(std::memory_order_relaxed)) { bad_scans = true; break; }
+        }
+        CUP(enqueue_piece(k));
+    }
+    pack_finish();
+    if (bad_scans) {
+        // the kernel is waiting for pieces that will not come: raise its give-up flag, drain, report
+        CUA(cudaMemcpyAsync(d_passes + B, h->seg_vals_pinned + 1, sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+        return align_abort(h, fail(ICPB_EINVAL, "scan table holds non-finite coordinates%s"));
+    }
+    CUA(cudaEventRecord(h->done_ev[0], cs));
+    CUA(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
+    CUA(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
     const double t_enq = trace ? now_us() : 0.0;
-    CU(cudaStreamSynchronize(cp));
+    CUA(cudaStreamSynchronize(cp));
     if (tP[B] != 0) {
         // a CTA gave up waiting for its scans (see the kernel): by now the whole table is resident,
         // so run the batch again without the streaming protocol
-        rc = launch(h, h->xy, h->offsets, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
-                    d_T, d_err, d_passes, nullptr, nullptr, cp);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
-        CU(cudaStreamSynchronize(cp));
+        rc = launch(h, d_xy, d_off, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
+                    d_T, d_err, d_passes, nullptr, nullptr, cp, 0, nullptr, nullptr, ep);
+        if (rc) return align_abort(h, rc);
+        CUA(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+        CUA(cudaStreamSynchronize(cp));
     }
+    // only now does the handle own the new table
+    h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
     const double t_sync = trace ? now_us() : 0.0;
     if (T_ld == 6) {
         memcpy(h_T, tT, nbI);
@@ -702,6 +1018,71 @@ int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offse
         fprintf(stderr, "[icpb_align_host] prep %.0f us, enqueue %.0f us, wait %.0f us, scatter %.0f us (%d segments)\n",
                 t_prep - t_entry, t_enq - t_prep, t_sync - t_enq, now_us() - t_sync, nseg);
     return 0;
+#undef CUP
+}
+
+int align_check(icpb_handle h, int64_t n_scans, const int32_t *h_pairs, int32_t init_ld, int64_t B,
+                const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
+                const icpb_epilogue *ep)
+{
+    if (!h || n_scans <= 0) return fail(ICPB_EINVAL, "icpb_align_host: bad argument%s");
+    if ((init_ld != 6 && init_ld != 9) || (T_ld != 6 && T_ld != 9))
+        return fail(ICPB_EINVAL, "icpb_align_host: init_ld / T_ld must be 6 (2x3 rows) or 9 (3x3)%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if ((rc = check_epilogue(ep, p))) return rc;
+    if (p->pair_mode != 0 || p->hist_cap > 0 || p->corr_stride > 0)
+        return fail(ICPB_EINVAL, "icpb_align_host: explicit pairs, no history/correspondences (use upload + run)%s");
+    if (B >= (int64_t(1) << 31)) return fail(ICPB_EINVAL, "icpb_align_host: at most 2^31 - 1 pairs per call%s");
+    if (B > 0 && (!h_pairs || !h_T || !h_err || !h_passes)) return fail(ICPB_EINVAL, "null pointer%s");
+    return 0;
+}
+
+}  // namespace
+
+int icpb_align_host_ex(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                       const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                       const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
+                       const icpb_epilogue *ep)
+{
+    if (!h_xy || !h_offsets) return fail(ICPB_EINVAL, "icpb_align_host: bad argument%s");
+    int rc = align_check(h, n_scans, h_pairs, init_ld, B, p, h_T, T_ld, h_err, h_passes, ep);
+    if (rc) return rc;
+    int64_t longest = 0;
+    if ((rc = validate_offsets(h_offsets, n_scans, &longest))) return rc;
+    TableSrc src;
+    src.xy = h_xy; src.offsets = h_offsets;
+    return align_impl(h, src, n_scans, longest, h_pairs, h_init, init_ld, B, p, h_T, T_ld, h_err, h_passes, ep);
+}
+
+int icpb_align_host_scans(icpb_handle h, const double *const *scan_xy, const int64_t *scan_len, int64_t n_scans,
+                          const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                          const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
+                          const icpb_epilogue *ep)
+{
+    if (!scan_xy || !scan_len) return fail(ICPB_EINVAL, "icpb_align_host_scans: bad argument%s");
+    int rc = align_check(h, n_scans, h_pairs, init_ld, B, p, h_T, T_ld, h_err, h_passes, ep);
+    if (rc) return rc;
+    std::vector<int64_t> offsets((size_t)n_scans + 1);
+    offsets[0] = 0;
+    int64_t longest = 0;
+    for (int64_t s = 0; s < n_scans; ++s) {
+        if (!scan_xy[s] || scan_len[s] <= 0)
+            return fail(ICPB_EINVAL, "empty scan in the list (the reference's argmin raises on it)%s");
+        offsets[(size_t)s + 1] = offsets[(size_t)s] + scan_len[s];
+        if (scan_len[s] > longest) longest = scan_len[s];
+    }
+    TableSrc src;
+    src.scan_xy = scan_xy; src.offsets = offsets.data();
+    return align_impl(h, src, n_scans, longest, h_pairs, h_init, init_ld, B, p, h_T, T_ld, h_err, h_passes, ep);
+}
+
+int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                       const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                       const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes)
+{
+    return icpb_align_host_ex(h, h_xy, h_offsets, n_scans, h_pairs, h_init, init_ld, B, p, h_T, T_ld, h_err, h_passes,
+                              nullptr);
 }
 
 int icpb_align_host(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
@@ -727,7 +1108,7 @@ int icpb_icp_pair_host(icpb_handle h, const double *h_src_xy, int64_t n_src,
         return fail(ICPB_EINVAL, "corr buffer missing or shorter than the source cloud%s");
     icpb_params q = *p;
     q.pair_mode = 0; q.k_first = 0; q.k_block = 1; q.k_stride = 0;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t nb = sizeof(double) * 2 * (size_t)(n_src + n_dst);
     if ((rc = h->s_pair_xy.reserve(nb))) return rc;
     if ((rc = h->s_pair_off.reserve(sizeof(int64_t) * 3))) return rc;
@@ -747,7 +1128,7 @@ int icpb_fit_pairs_host(icpb_handle h, const double *h_a_xy, const double *h_b_x
 {
     if (!h || !h_a_xy || !h_b_xy || n <= 0 || n > 0x7fffffff || !h_T6 || !h_err)
         return fail(ICPB_EINVAL, "icpb_fit_pairs_host: bad argument%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     int rc;
     const size_t nb = sizeof(double) * 2 * (size_t)n;
     if ((rc = h->s_pair_xy.reserve(2 * nb))) return rc;
@@ -783,7 +1164,7 @@ int icpb_proximity_closest(icpb_handle h, const double *h_xy, const double *h_tr
 {
     if (!h || !h_xy || !h_travelled || n <= 0 || n > 0x3fffffff || !h_closest || !h_dist)
         return fail(ICPB_EINVAL, "icpb_proximity_closest: bad argument%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     double *d_xy, *d_trav;
     int rc = upload_poses(h, h_xy, h_travelled, n, &d_xy, &d_trav);
     if (rc) return rc;
@@ -807,7 +1188,7 @@ int icpb_proximity_pairs(icpb_handle h, const double *h_xy, const double *h_trav
     if (!h || !h_xy || !h_travelled || n <= 0 || n > 0x3fffffff || !n_pairs || capacity < 0 ||
         (capacity > 0 && !h_pairs))
         return fail(ICPB_EINVAL, "icpb_proximity_pairs: bad argument%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     double *d_xy, *d_trav;
     int rc = upload_poses(h, h_xy, h_travelled, n, &d_xy, &d_trav);
     if (rc) return rc;
@@ -884,7 +1265,7 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
         }
     }
     if (ve.empty() || n_steps == 0) return 0;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t E = ve.size() / 2, N = (size_t)n;
     // [poses 3N | tf 6E | dW 4E | PB 6E | M 3N | P 3N] doubles, then [edges 2E] int32
     const size_t n_dbl = 3 * N + 6 * E + 4 * E + 6 * E + 3 * N + 3 * N;
@@ -905,10 +1286,8 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
     const size_t node_cap = smem_cap / (3 * sizeof(double));
     const size_t scan_bytes = sizeof(double) * 3 * icpb::kSgdThreads;
     int csize = (int)((N + node_cap - 1) / node_cap);
-    if (const char *t = getenv("ICPB_SGD_CLUSTER")) {        // tests: force a cluster size
-        const int v = atoi(t);
-        if (v >= 1 && v <= 8 && (size_t)v * node_cap >= N) csize = v;
-    }
+    if (h->tune_sgd_cluster >= 1 && h->tune_sgd_cluster <= 8 && (size_t)h->tune_sgd_cluster * node_cap >= N)
+        csize = h->tune_sgd_cluster;                             // icpb_set_tuning("sgd_cluster"), tests
     a.poses_in_smem = csize <= 8 ? 1 : 0;
     if (!a.poses_in_smem) csize = 1;
     a.slice = (int32_t)((N + csize - 1) / csize);
@@ -974,7 +1353,7 @@ int icpb_occupancy_grid_bounds(icpb_handle h, const double *h_poses, int64_t n, 
     int rc = grid_check(h, h_poses, n, cell_width, "icpb_occupancy_grid_bounds");
     if (rc) return rc;
     if (!min_x_out || !min_y_out || !height || !width) return fail(ICPB_EINVAL, "icpb_occupancy_grid_bounds: null output%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if ((rc = h->s_grid.reserve(sizeof(double) * 4 * (size_t)n + 4 * sizeof(unsigned long long)))) return rc;
     unsigned long long *d_mm = (unsigned long long *)h->s_grid.p;
     double *d_poses = (double *)(d_mm + 4);
@@ -1014,7 +1393,7 @@ int icpb_occupancy_grid_update(icpb_handle h, const double *h_poses, int64_t n, 
     // the per-cell closed form needs a miss to leave a cell negative and a hit to leave it positive
     if (k_hit < 1 || k_hit > 127 || k_miss < 1 || k_miss > 127)
         return fail(ICPB_EINVAL, "icpb_occupancy_grid_update: kHitOdds and kMissOdds must be integers in 1..127%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     // the beam order keys are 32 bit: 2 * (beam index + 1) + 1 must fit (2^31 - 2 beams)
     int64_t n_points = 0;
     CU(cudaMemcpy(&n_points, h->offsets + n, sizeof n_points, cudaMemcpyDeviceToHost));
@@ -1048,7 +1427,7 @@ int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out)
 {
     if (!h || !out) return fail(ICPB_EINVAL, "icpb_get_kernel_info: bad argument%s");
     if (!h->xy) return fail(ICPB_ENOSCANS, "no scan table set%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     LaunchCfg cfg;
     kernel_fn fn = pick_kernel(nullptr);
     int rc = make_cfg(h, h->longest, B > 0 ? B : (int64_t)1 << 40, &cfg, fn);
@@ -1065,10 +1444,12 @@ int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out)
 
 int64_t icpb_launch_count(icpb_handle h) { return h ? h->launches : 0; }
 
+int64_t icpb_scan_count(icpb_handle h) { return h && h->xy ? h->n_scans : 0; }
+
 int icpb_count_work(icpb_handle h, int enable)
 {
     if (!h) return fail(ICPB_EINVAL, "handle is null%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (enable) {
         CU(cudaMemset(h->queue + kQueueRing, 0, sizeof(unsigned long long)));
         h->executed = h->queue + kQueueRing;
@@ -1081,7 +1462,7 @@ int icpb_count_work(icpb_handle h, int enable)
 int icpb_read_work(icpb_handle h, uint64_t *executed_pde)
 {
     if (!h || !executed_pde) return fail(ICPB_EINVAL, "icpb_read_work: bad argument%s");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(cudaDeviceSynchronize());
     unsigned long long v = 0;
     CU(cudaMemcpy(&v, h->queue + kQueueRing, sizeof v, cudaMemcpyDeviceToHost));

@@ -29,7 +29,21 @@ namespace icpb {
 constexpr int   kChunk    = 16;        // targets per bookkeeping chunk
 constexpr float kPadCoord = 1.0e15f;   // coordinates of padding targets (distance ~2e30, never a candidate)
 constexpr int   kMaxWarps = 32;
-constexpr int   kNumSums  = 9;
+constexpr int   kNumSums  = 8;        // 7 fp64 sums per reduction tile (+1 pad): see kS* below
+// columns of a tile's partial sums (a = moved source point - c, b = matched target - g):
+enum { kSbx = 0, kSby = 1, kSaxbx = 2, kSaxby = 3, kSaybx = 4, kSayby = 5, kSerr = 6 };
+constexpr int   kTw       = 8;        // doubles per warp-private transform record: T[6], sigma, -
+// Pruning granularity: a warp's 64 source points are split into kGroups groups of consecutive lanes;
+// every group has its own bounding circle, upper bound and list of target chunks, and in a sweep step
+// each group reads its own next chunk (kGroups distinct shared-memory addresses per load).  Measured
+// chunk steps per 64-point tile on the 1,024-beam chain: 6.3 with one group, 4.3 with two, 3.3 with
+// four, 2.9 with eight (the step count is the maximum over the groups).
+#ifndef ICPB_G
+#define ICPB_G 4
+#endif
+constexpr int   kGroups   = ICPB_G;
+constexpr int   kLpg      = 32 / kGroups;   // lanes per group
+static_assert(kGroups == 1 || kGroups == 2 || kGroups == 4 || kGroups == 8, "kGroups must be 1, 2, 4 or 8");
 
 struct KernelArgs {
     const double  *xy;        // scan table, (sum m_i, 2) fp64
@@ -59,9 +73,23 @@ struct KernelArgs {
     // fused gather (multi-GPU): every finished pair's 8-double constraint record
     // [T(6), error, passes] is stored straight into every rank's gather buffer over NVLink peer
     // memory, at row rec_row0 + pair id; peers[r] is rank r's buffer as mapped in this process
+    // row = rec_row0 + (pid / rec_block) * rec_stride + pid % rec_block, so a rank that owns
+    // interleaved blocks of the problem index space (dist.shard_indices) writes global rows
     double *const *peers;
     int32_t n_peers;
-    int64_t rec_row0;
+    int64_t rec_row0, rec_block, rec_stride;
+    // acceptance epilogue (reference src/loop_closure_detection.py:35-39,155-159):
+    // pairs with error < accept_thresh append their record [T(6), error, (row << 16) | passes] to
+    // accept_rec (this rank's region of every peer's buffer when accept_peers is set) in completion
+    // order; the last CTA to leave publishes the count
+    double   accept_thresh;
+    double  *accept_rec;              // local buffer, accept_cap rows of 8 doubles (or nullptr)
+    double *const *accept_peers;      // n_peers buffers (each world * accept_cap rows) or nullptr
+    unsigned long long *accept_ctr;   // [0] rows appended, [1] CTAs that have left
+    long long *accept_count_out;      // local: final count; with peers: slot accept_rank of every peer's counts
+    long long *const *accept_count_peers;
+    int64_t  accept_cap;
+    int32_t  accept_rank;
 };
 
 // ---- fp32 filter distance: one definition, used by the sweep and by the refine step ----------
@@ -121,22 +149,28 @@ __device__ __forceinline__ float min3f(float a, float b, float c)
     return fminf(fminf(a, b), c);
 }
 
-// MUFU square root (1-2 ulp); every use below carries a much larger safety factor
+// MUFU square root (1-2 ulp, denormal inputs flushed to zero).  Every use below carries a much larger
+// safety factor; a flushed argument (< 1.2e-38) costs at most 8.7e-19 e in decision_thr, which its
+// 16 e^2 + 1e-30 terms cover for every e, and the other uses take decision_thr's result (>= 1e-30).
 __device__ __forceinline__ float sqrt_fast(float x)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
-// Bound on |fp32 filter distance - exact distance| doubled, as a function of the best filter
-// distance m1.  e bounds the error of one coordinate difference: both inputs were rounded to
-// fp32 (relative 2^-24 each) and the subtraction rounds once more.
-__device__ __forceinline__ float filter_tol(float m1, float px, float py, float qmax)
+// Bound on |fp32 filter distance - exact distance|, doubled, as a function of the best filter
+// distance m1: 8 sqrt(m1) e + 16 e^2 + 16 u m1, where e bounds the error of one coordinate difference
+// (both inputs were rounded to fp32, relative 2^-24 each, and the subtraction rounds once more).
+// Decision threshold of a point whose best filter distance is m1: m1 plus the doubled rounding bound,
+// times (1 + 8u) for the sign-bit form of the candidate test (dist32x4_minus), plus an absolute 1e-30
+// so that the threshold is positive (a zero filter distance is a candidate) and fp32 underflow of
+// the squares (coordinates below ~1e-15) only ever adds candidates.  e is the bound on one
+// coordinate difference (2u (|p|max + |q|max), u = 2^-24), taken once per tile from the tile's
+// largest coordinate, so it is >= the bound of every point in it.
+__device__ __forceinline__ float decision_thr(float m1, float e)
 {
-    const float u = 5.9604645e-8f;                              // 2^-24
-    const float e = 2.0f * u * (fmaxf(fabsf(px), fabsf(py)) + qmax) * 1.0001f;
-    return 8.0f * sqrt_fast(m1) * e + 16.0f * e * e + 16.0f * u * m1;
+    return fmaf(m1, 1.000002f, fmaf(8.0f * sqrt_fast(m1), e, fmaf(16.0f * e, e, 1e-30f)));
 }
 
 // Rare path of the decision step: all targets j in [lo, hi) whose filter distance is <= thr are
@@ -230,6 +264,20 @@ __device__ __forceinline__ float warp_max_nonneg(float v)
     return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
+// max / min over the lanes of one pruning group (kLpg consecutive lanes); every lane gets the result
+__device__ __forceinline__ float group_max(float v)
+{
+#pragma unroll
+    for (int o = kLpg / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float group_min(float v)
+{
+#pragma unroll
+    for (int o = kLpg / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // Butterfly reduction of 8 doubles across the warp: each level halves the number of values a lane
 // carries (lanes exchange the half they do not keep), then two plain levels finish.  9 double
 // shuffles instead of 40.  Afterwards lane L holds the warp total of value
@@ -267,13 +315,46 @@ __device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
     return w1;
 }
 
+// filter distance minus a threshold, for the decision step's candidate test: the sign bit of
+// e = fl(dy*dy + fl(dx*dx - thr)) is set whenever the sweep's filter distance fl(dy*dy + fl(dx*dx))
+// is <= thr / (1 + 8u) (u = 2^-24): with s = dx*dx + dy*dy <= thr (1 + 3u) / (1 + 8u) the exact value
+// s - thr is below -4u thr, and the one rounding before the sign is taken moves it by at most
+// u max(dx*dx, thr).  Same four packed instructions as a distance.
+__device__ __forceinline__ void dist32x4_minus(u64 PX, u64 PY, u64 NTHR, const float4 &X, const float4 &Y, float *e)
+{
+    const u64 dxa = sub2(pack2(X.x, X.y), PX), dya = sub2(pack2(Y.x, Y.y), PY);
+    const u64 dxb = sub2(pack2(X.z, X.w), PX), dyb = sub2(pack2(Y.z, Y.w), PY);
+    unpack2(fma2(dya, dya, fma2(dxa, dxa, NTHR)), e[0], e[1]);
+    unpack2(fma2(dyb, dyb, fma2(dxb, dxb, NTHR)), e[2], e[3]);
+}
+
+// Largest singular value of the linear part of T (a bound on how much T stretches a distance), as
+// a float with a safety factor.  1 for the rigid transforms ICP composes; the caller's initial
+// guess may be any affine map with bottom row [0 0 1].
+__device__ __forceinline__ double stretch_of(const double *T)
+{
+    const float a = (float)T[0], b = (float)T[1], c = (float)T[3], d = (float)T[4];
+    const float f2 = a * a + b * b + c * c + d * d;
+    const float det = a * d - b * c;
+    const float disc = fmaxf(f2 * f2 - 4.0f * det * det, 0.0f);
+    return (double)(sqrtf(0.5f * (f2 + sqrtf(disc))) * 1.00002f + 1e-30f);
+}
+
 // PRUNE = false: exhaustive sweep over every chunk (the reference's brute force; used for the
 // FP32-pipe roofline characterisation).  PRUNE = true: exact chunk pruning (the product default).
 //
-// Shared memory: target SoA | chunk circles | correspondences | red[2][tiles][9] | Tw[warps][6]
+// Shared memory: target SoA | chunk circles | tile circles | mm[2][tiles] | correspondences |
+//                red[2][tiles][8] | Tw[warps][8] | S0[2]
 // A tile = 32*R consecutive source points = one warp's register tile.  Warps pull tiles from a
 // shared counter (tiles differ in how many chunks survive pruning); partial sums are stored per
-// tile and folded in tile order, so the result does not depend on which warp ran which tile.
+// 64-point reduction tile and folded in tile order, so the result does not depend on which warp ran
+// which tile.
+//
+// Per pair, once: the bounding circle of every tile's UNTRANSFORMED source points and
+// S0 = sum(p_i - p_0).  A pass then gets the tile's circle as (T centre, stretch(T) radius) and the
+// sum of the moved, shifted source points as A S0 (A = linear part of T) instead of reducing them
+// again: only the largest upper bound of the tile and the 7 sums that depend on the matches are
+// reduced per pass.
 //
 // CLUSTER = true (latency mode, few problems): one thread-block *cluster* of up to 8 CTAs per scan
 // pair.  Every CTA stages the target itself; the source tiles are dealt round-robin to the CTAs
@@ -284,24 +365,27 @@ template <int R, bool PRUNE, bool CLUSTER>
 #ifndef ICPB_MIN_CTAS
 #define ICPB_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, (R >= 4 ? 2 : ICPB_MIN_CTAS))
+__global__ void __launch_bounds__(256, (CLUSTER ? 1 : (R >= 4 ? 2 : ICPB_MIN_CTAS)))
 icp_align_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float  *tqx    = reinterpret_cast<float *>(smem_raw);
     float  *tqy    = tqx + a.n2pad_cap;
     float4 *cb     = reinterpret_cast<float4 *>(tqy + a.n2pad_cap);          // chunk circle (cx, cy, r, -)
-    int    *corr_s = reinterpret_cast<int *>(cb + a.nchunk_cap);
-    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // [2][ntile_cap][9]
-    double *Tw     = red + 2 * a.ntile_cap * kNumSums;                       // [kMaxWarps][6] per-warp copy of T
+    float4 *tc     = cb + a.nchunk_cap;                                      // tile circle, untransformed source
+    int2   *mm     = reinterpret_cast<int2 *>(tc + a.ntile_cap * kGroups);             // [2][ntile_cap] (min, max) matched index per tile
+    int    *corr_s = reinterpret_cast<int *>(mm + 2 * a.ntile_cap);
+    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // [2][ntile_cap][8]
+    double *Tw     = red + 2 * a.ntile_cap * kNumSums;                       // [kMaxWarps][8] per-warp copy of T
+    double *S0     = Tw + kMaxWarps * kTw;                                   // sum of (source - first source point)
     __shared__ long long s_pid;
     __shared__ unsigned int s_qmax_bits;
     __shared__ int s_tile_ctr[2];
 
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const float kInf = __int_as_float(0x7f800000);
-    double *Tmine = Tw + warp * 6;
+    double *Tmine = Tw + warp * kTw;
     unsigned int executed = 0;
     namespace cg = cooperative_groups;
     int crank = 0, csize = 1;
@@ -374,11 +458,13 @@ icp_align_kernel(const KernelArgs a)
         static_assert(R % 2 == 0, "R must be even");
         const int ntiles = (n1 + 63) / 64;                 // reduction tiles
         const int nwork = (ntiles + SUBT - 1) / SUBT;            // warp work items
+        const double2 g = dst[0];                 // shifts for the one-pass covariance sums
+        const double2 s0 = src[0];
 
         // ---------------- stage the target in shared memory as fp32 SoA ----------------
         {
             float qm = 0.0f;
-            for (int j = tid; j < n2pad; j += NT) {
+            for (int j = tid; j < n2pad + kChunk; j += NT) {     // + one all-padding chunk (index nchunks)
                 float x = kPadCoord, y = kPadCoord;
                 if (j < n2) {
                     const double2 q = dst[j];
@@ -395,6 +481,49 @@ icp_align_kernel(const KernelArgs a)
             if (a.p.rotation_only && (lane == 2 || lane == 5)) v = 0.0;     // src/icp.py:60-61
             Tmine[lane] = v;
         }
+        // ---------------- per work item: circle of the untransformed source points, S0 partials -------
+        // (the partials go to the second half of `red`, which the passes use from pass 1 on)
+        for (int w = warp; w < nwork; w += nwarps) {
+            float lx = kInf, ly = kInf, hx = -kInf, hy = -kInf;
+            float sx[R], sy[R];
+#pragma unroll
+            for (int sub = 0; sub < SUBT; ++sub) {
+                double ax = 0.0, ay = 0.0;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = sub * 2 + rr;
+                    const int i = ((w * SUBT + sub) * 32 + lane) * 2 + rr;
+                    const double2 s = src[min(i, n1 - 1)];       // lanes past the end repeat the last point
+                    sx[r] = (float)s.x; sy[r] = (float)s.y;
+                    if (i < n1) { ax += s.x - s0.x; ay += s.y - s0.y; }
+                }
+                const int rt = w * SUBT + sub;
+                if (rt < ntiles) {                               // warp-uniform
+                    ax = warp_sum(ax); ay = warp_sum(ay);
+                    if (lane == 0) {
+                        red[(a.ntile_cap + rt) * kNumSums] = ax;
+                        red[(a.ntile_cap + rt) * kNumSums + 1] = ay;
+                    }
+                }
+            }
+            if (PRUNE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    lx = fminf(lx, sx[r]); hx = fmaxf(hx, sx[r]);
+                    ly = fminf(ly, sy[r]); hy = fmaxf(hy, sy[r]);
+                }
+                lx = group_min(lx); ly = group_min(ly); hx = group_max(hx); hy = group_max(hy);
+                const float ccx = 0.5f * (lx + hx), ccy = 0.5f * (ly + hy);
+                float r2 = 0.0f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) r2 = fmaxf(r2, dist32(ccx, ccy, sx[r], sy[r]));
+                r2 = group_max(r2);
+                // fp32 rounding of the points and of the centre: a few ulps of the largest coordinate
+                const float smax = fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy)));
+                if ((lane & (kLpg - 1)) == 0)
+                    tc[w * kGroups + lane / kLpg] = make_float4(ccx, ccy, sqrtf(r2) * 1.0001f + 4.8e-7f * smax, 0.0f);
+            }
+        }
         __syncthreads();
         const float qmax = __uint_as_float(s_qmax_bits);
         // ---------------- bounding circle of every 16-target chunk ----------------
@@ -410,8 +539,15 @@ icp_align_kernel(const KernelArgs a)
             for (int j = j0; j < j1; ++j) r2 = fmaxf(r2, dist32(cx, cy, tqx[j], tqy[j]));
             cb[c] = make_float4(cx, cy, sqrtf(r2) * 1.00001f, 0.0f);
         }
-        const double2 g = dst[0];                 // shifts for the one-pass covariance sums
-        const double2 s0 = src[0];
+        if (tid == NT - 1) {                                      // fixed order: tile 0, 1, 2, ...
+            double ax = 0.0, ay = 0.0;
+            for (int t = 0; t < ntiles; ++t) {
+                ax += red[(a.ntile_cap + t) * kNumSums];
+                ay += red[(a.ntile_cap + t) * kNumSums + 1];
+            }
+            S0[0] = ax; S0[1] = ay;
+        }
+        if (lane == 0) Tmine[6] = stretch_of(Tmine);
         __syncthreads();
 
         int passes = 0, iteration = 0;
@@ -420,6 +556,7 @@ icp_align_kernel(const KernelArgs a)
 
         for (;;) {
             double *redp = red + (passes & 1) * a.ntile_cap * kNumSums;
+            int2 *mmp = mm + (passes & 1) * a.ntile_cap;
 
             for (;;) {
                 int tile = 0;
@@ -429,39 +566,69 @@ icp_align_kernel(const KernelArgs a)
                 if (tile >= nwork) break;
                 // point r of this lane: reduction tile tile*SUBT + r/2, lane's pair of consecutive points
                 auto pidx = [&](int r) { return ((tile * SUBT + (r >> 1)) * 32 + lane) * 2 + (r & 1); };
-                // ---- transform, upper bounds, tile bounding circle ----
+                // ---- transform ----
                 float px[R], py[R];
-                float ubmax = 0.0f, lx = kInf, ly = kInf, hx = -kInf, hy = -kInf;
-                {
-                    double T[6];
+                double T[6];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
+                for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int i = min(pidx(r), n1 - 1);      // lanes past the end repeat the last point
-                        const double2 s = src[i];
-                        double X, Y;
-                        apply_T(T, s.x, s.y, X, Y);
-                        px[r] = (float)X; py[r] = (float)Y;
-                    }
+                for (int r = 0; r < R; ++r) {
+                    const int i = min(pidx(r), n1 - 1);      // lanes past the end repeat the last point
+                    const double2 s = src[i];
+                    double X, Y;
+                    apply_T(T, s.x, s.y, X, Y);
+                    px[r] = (float)X; py[r] = (float)Y;
                 }
-                float tcx = 0.f, tcy = 0.f, reach = kInf;
-                if (PRUNE) {
-                    // bounding circle of the tile's points
+                // ---- group circle, upper bounds, reach (per pruning group of kLpg lanes) ----
+                float tol_e = 0.f;                               // per-coordinate rounding bound of the group
+                float m1[R], m2[R];
+                int c1[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { m1[r] = kInf; m2[r] = kInf; c1[r] = 0; }
+                const float4 *qx4 = reinterpret_cast<const float4 *>(tqx);
+                const float4 *qy4 = reinterpret_cast<const float4 *>(tqy);
+                // smallest filter distance of point r to the 16 targets of a staged chunk
+                auto chunk_min = [&](const float4 (&X)[4], const float4 (&Y)[4], int r) -> float {
+                    float d[16];
+                    const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
+                    float cm = min3f(d[0], d[1], d[2]);
+                    cm = min3f(cm, d[3], d[4]);
+                    cm = min3f(cm, d[5], d[6]);
+                    cm = min3f(cm, d[7], d[8]);
+                    cm = min3f(cm, d[9], d[10]);
+                    cm = min3f(cm, d[11], d[12]);
+                    cm = min3f(cm, d[13], d[14]);
+                    return fminf(cm, d[15]);
+                };
+                // one sweep step: chunk c (per lane: the lanes of a group agree, groups differ)
+                auto sweep = [&](int c) {
+                    float4 X[4], Y[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        lx = fminf(lx, px[r]); hx = fmaxf(hx, px[r]);
-                        ly = fminf(ly, py[r]); hy = fmaxf(hy, py[r]);
+                        const float cm = chunk_min(X, Y, r);
+                        const bool better = cm < m1[r];
+                        m2[r] = fminf(m2[r], better ? m1[r] : cm);
+                        m1[r] = fminf(m1[r], cm);
+                        c1[r] = better ? c : c1[r];
                     }
-                    lx = warp_min(lx); ly = warp_min(ly); hx = warp_max(hx); hy = warp_max(hy);
-                    tcx = 0.5f * (lx + hx); tcy = 0.5f * (ly + hy);
-                    float rho2 = 0.0f;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) rho2 = fmaxf(rho2, dist32(tcx, tcy, px[r], py[r]));
-                    rho2 = warp_max_nonneg(rho2);
+                };
+                if (PRUNE) {
+                    const int grp = lane / kLpg, li = lane & (kLpg - 1);
+                    const float4 c0 = tc[tile * kGroups + grp];
+                    double X, Y;
+                    apply_T(T, (double)c0.x, (double)c0.y, X, Y);
+                    const float tcx = (float)X, tcy = (float)Y;
+                    const float rho = (float)Tmine[6] * c0.z;
+                    // largest coordinate magnitude of the group's moved points
+                    const float pmax = fmaxf(fabsf(tcx), fabsf(tcy)) * 1.000001f + rho;
+                    tol_e = 2.0f * 5.9604645e-8f * (pmax + qmax) * 1.0001f;
                     // upper bound of every point's nearest-neighbour filter distance: its distance to
                     // a real target -- the previous pass's match, or on the first pass the best
-                    // target in the chunks around the chunk centre nearest to the tile centre
+                    // target in the chunks around the chunk centre nearest to the group centre
                     float ub[R];
                     if (passes > 0) {
 #pragma unroll
@@ -471,100 +638,79 @@ icp_align_kernel(const KernelArgs a)
                         }
                     } else {
                         unsigned key = 0xffffffffu;
-                        for (int c = lane; c < nchunks; c += 32) {
+                        for (int c = li; c < nchunks; c += kLpg) {
                             const float4 bc = cb[c];
                             const unsigned k = (__float_as_uint(dist32(tcx, tcy, bc.x, bc.y)) & 0xfffff000u) | (unsigned)min(c, 4095);
                             key = min(key, k);
                         }
-                        const int cstar = (int)(__reduce_min_sync(0xffffffffu, key) & 0xfffu);
+#pragma unroll
+                        for (int o = kLpg / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+                        const int cstar = (int)(key & 0xfffu);
 #pragma unroll
                         for (int r = 0; r < R; ++r) ub[r] = kInf;
-                        const float4 *qx4 = reinterpret_cast<const float4 *>(tqx);
-                        const float4 *qy4 = reinterpret_cast<const float4 *>(tqy);
-                        for (int c = max(cstar - 1, 0); c <= min(cstar + 1, nchunks - 1); ++c) {
-                            float4 X[4], Y[4];
+                        for (int dc = -1; dc <= 1; ++dc) {
+                            int c = cstar + dc;
+                            if (c < 0 || c >= nchunks) c = nchunks;      // the all-padding chunk
+                            float4 X4[4], Y4[4];
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
+                            for (int v = 0; v < 4; ++v) { X4[v] = qx4[4 * c + v]; Y4[v] = qy4[4 * c + v]; }
 #pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                float d[16];
-                                const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
-#pragma unroll
-                                for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
-                                float cm = min3f(d[0], d[1], d[2]);
-                                cm = min3f(cm, d[3], d[4]);   cm = min3f(cm, d[5], d[6]);
-                                cm = min3f(cm, d[7], d[8]);   cm = min3f(cm, d[9], d[10]);
-                                cm = min3f(cm, d[11], d[12]); cm = min3f(cm, d[13], d[14]);
-                                ub[r] = fminf(ub[r], fminf(cm, d[15]));
-                            }
+                            for (int r = 0; r < R; ++r) ub[r] = fminf(ub[r], chunk_min(X4, Y4, r));
                         }
                     }
+                    float ubmax = 0.0f;
 #pragma unroll
                     for (int r = 0; r < R; ++r) ubmax = fmaxf(ubmax, ub[r]);
-                    ubmax = warp_max_nonneg(ubmax);
-                    // the decision threshold of any point of the tile is at most ubmax + tol(ubmax)
-                    // (filter_tol grows with the distance and with the coordinate magnitudes)
-                    const float pmax = fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy)));
-                    ubmax += filter_tol(ubmax, pmax, pmax, qmax);
-                    // every target within sqrt(ubmax) of some point of the tile lies within `reach`
-                    // of the tile centre; e covers the fp32 rounding of the centres and differences
+                    ubmax = group_max(ubmax);
+                    // the decision threshold of any point of the group is at most ubmax + tol(ubmax)
+                    // (the tolerance grows with the distance and with the coordinate magnitudes)
+                    ubmax = decision_thr(ubmax, tol_e);
+                    // every target within sqrt(ubmax) of some point of the group lies within `reach`
+                    // of the group centre; e covers the fp32 rounding of the centres and differences
                     const float e = 4.0f * 1.1920929e-7f * (pmax + qmax);
-                    reach = (sqrt_fast(rho2) + sqrt_fast(ubmax)) * 1.0001f + e;
-                }
+                    const float reach = (rho + sqrt_fast(ubmax)) * 1.0001f + 2.0f * e;
 
-                float m1[R], m2[R];
-                int c1[R];
+                    for (int cbase = 0; cbase < nchunks; cbase += 32) {
+                        // chunks of this block that the group has to sweep: lane li of the group tests
+                        // chunks cbase + li, cbase + kLpg + li, ... against the group's circle
+                        unsigned mask = 0;
 #pragma unroll
-                for (int r = 0; r < R; ++r) { m1[r] = kInf; m2[r] = kInf; c1[r] = 0; }
-
-                const float4 *qx4 = reinterpret_cast<const float4 *>(tqx);
-                const float4 *qy4 = reinterpret_cast<const float4 *>(tqy);
-                for (int cbase = 0; cbase < nchunks; cbase += 32) {
-                    unsigned need;
-                    {
-                        const int c = cbase + lane;
-                        bool nd = c < nchunks;
-                        if (PRUNE && nd) {
-                            const float4 b = cb[c];
-                            const float lim = (reach + b.z) * 1.00001f;
-                            nd = dist32(tcx, tcy, b.x, b.y) <= lim * lim;
+                        for (int j = 0; j < kGroups; ++j) {
+                            const int c = cbase + j * kLpg + li;
+                            bool nd = c < nchunks;
+                            if (nd) {
+                                const float4 b = cb[c];
+                                const float lim = (reach + b.z) * 1.00001f;
+                                nd = dist32(tcx, tcy, b.x, b.y) <= lim * lim;
+                            }
+                            const unsigned bal = __ballot_sync(0xffffffffu, nd);
+                            if (kGroups == 1) mask = bal;
+                            else mask |= ((bal >> (grp * kLpg)) & ((1u << (kLpg & 31)) - 1u)) << ((j * kLpg) & 31);
                         }
-                        need = __ballot_sync(0xffffffffu, nd);
-                    }
-                    executed += (unsigned)__popc(need);
+                        // the warp takes as many steps as its busiest group; a group that has run out of
+                        // chunks sweeps the all-padding chunk (index nchunks), which changes nothing
+                        const int steps = __reduce_max_sync(0xffffffffu, __popc(mask));
+                        executed += (unsigned)steps;
 #pragma unroll 1
-                    while (need) {
-                        const int c = cbase + __ffs(need) - 1;
-                        need &= need - 1;
-                        float4 X[4], Y[4];
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) { X[v] = qx4[4 * c + v]; Y[v] = qy4[4 * c + v]; }
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            float d[16];
-                            const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
-                            float cm = min3f(d[0], d[1], d[2]);
-                            cm = min3f(cm, d[3], d[4]);
-                            cm = min3f(cm, d[5], d[6]);
-                            cm = min3f(cm, d[7], d[8]);
-                            cm = min3f(cm, d[9], d[10]);
-                            cm = min3f(cm, d[11], d[12]);
-                            cm = min3f(cm, d[13], d[14]);
-                            cm = fminf(cm, d[15]);
-                            const bool better = cm < m1[r];
-                            m2[r] = fminf(m2[r], better ? m1[r] : cm);
-                            m1[r] = fminf(m1[r], cm);
-                            c1[r] = better ? c : c1[r];
+                        for (int st = 0; st < steps; ++st) {
+                            const int c = mask ? cbase + __ffs(mask) - 1 : nchunks;
+                            mask &= mask - 1;
+                            sweep(c);
                         }
                     }
+                } else {
+                    // no bound: the rounding bound of each point from the warp's largest coordinate
+                    float pm = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) pm = fmaxf(pm, fmaxf(fabsf(px[r]), fabsf(py[r])));
+                    pm = warp_max_nonneg(pm);
+                    tol_e = 2.0f * 5.9604645e-8f * (pm + qmax) * 1.0001f;
+                    executed += (unsigned)nchunks;
+#pragma unroll 1
+                    for (int c = 0; c < nchunks; ++c) sweep(c);
                 }
                 // ---- exact decision among the filter's candidates, then the fit sums ----
                 {
-                    double T[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
                     double cx, cy;                               // shift = transformed first source point
                     apply_T(T, s0.x, s0.y, cx, cy);
 #pragma unroll
@@ -572,6 +718,7 @@ icp_align_kernel(const KernelArgs a)
                     double sum[kNumSums];
 #pragma unroll
                     for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+                    int imin = 0x7fffffff, imax = -1;            // range of this lane's matched target indices
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
                         const int r = sub * 2 + rr;
@@ -580,52 +727,52 @@ icp_align_kernel(const KernelArgs a)
                             const double2 s = src[i];
                             double Px, Py;
                             apply_T(T, s.x, s.y, Px, Py);
-                            const float thr = m1[r] + filter_tol(m1[r], px[r], py[r], qmax);
+                            const float thr = decision_thr(m1[r], tol_e);
                             const int j0 = c1[r] * kChunk;
-                            // candidates inside the best chunk: how many, and where
-                            float d[16];
+                            // candidates inside the best chunk: sign bit of (distance - thr), shifted
+                            // into a mask one target at a time (bit 15 - k <-> target j0 + k)
+                            unsigned acc0 = 0, acc1 = 0;
                             {
                                 const float4 *bx = reinterpret_cast<const float4 *>(tqx + j0);
                                 const float4 *by = reinterpret_cast<const float4 *>(tqy + j0);
                                 const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
+                                const u64 NTHR = pack2(-thr, -thr);
+                                float e[16];
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) dist32x4(PX, PY, bx[v], by[v], d + 4 * v);
+                                for (int v = 0; v < 4; ++v) dist32x4_minus(PX, PY, NTHR, bx[v], by[v], e + 4 * v);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    acc0 = __funnelshift_l(__float_as_uint(e[k]), acc0, 1);
+                                    acc1 = __funnelshift_l(__float_as_uint(e[k + 8]), acc1, 1);
+                                }
                             }
-                            unsigned cand = 0;                   // bit k: target j0 + k is a candidate
-                            // one FSETP + one predicated LOP per target
-#define ICPB_CAND(K) asm("{ .reg .pred q; setp.le.f32 q, %1, %2; @q or.b32 %0, %0, %3; }" \
-                         : "+r"(cand) : "f"(d[K]), "f"(thr), "n"(1 << K))
-                            ICPB_CAND(0);  ICPB_CAND(1);  ICPB_CAND(2);  ICPB_CAND(3);
-                            ICPB_CAND(4);  ICPB_CAND(5);  ICPB_CAND(6);  ICPB_CAND(7);
-                            ICPB_CAND(8);  ICPB_CAND(9);  ICPB_CAND(10); ICPB_CAND(11);
-                            ICPB_CAND(12); ICPB_CAND(13); ICPB_CAND(14); ICPB_CAND(15);
-#undef ICPB_CAND
-                            static_assert(kChunk == 16, "candidate count is written out for 16 targets");
-                            int idx = j0 + __ffs(cand) - 1;      // unique candidate: no fp64 needed
+                            static_assert(kChunk == 16, "the candidate mask is written out for 16 targets");
+                            const unsigned acc = (acc0 << 8) | acc1;
+                            int idx = j0 + __clz((int)acc) - 16;  // unique candidate: no fp64 needed
                             if (m2[r] <= thr)                    // another chunk is within the bound
                                 idx = exact_decide_all(nchunks, n2, j0, thr, px[r], py[r], Px, Py, tqx, tqy, cb, dst);
-                            else if (cand & (cand - 1))          // more than one candidate in the chunk
-                                idx = exact_decide_chunk(j0, cand, Px, Py, dst);
-                            else if (cand == 0)                  // (non-finite input: keep a valid index)
+                            else if (acc & (acc - 1))            // more than one candidate in the chunk
+                                idx = exact_decide_chunk(j0, __brev(acc) >> 16, Px, Py, dst);
+                            else if (acc == 0)                   // (non-finite input: keep a valid index)
                                 idx = j0;
                             corr_s[i] = idx;
+                            imin = min(imin, idx); imax = max(imax, idx);
                             const double2 q = dst[idx];
                             const double ax = Px - cx, ay = Py - cy, bx = q.x - g.x, by = q.y - g.y;
-                            sum[0] += ax; sum[1] += ay; sum[2] += bx; sum[3] += by;
-                            sum[4] = fma(ax, bx, sum[4]); sum[5] = fma(ax, by, sum[5]);
-                            sum[6] = fma(ay, bx, sum[6]); sum[7] = fma(ay, by, sum[7]);
+                            sum[kSbx] += bx; sum[kSby] += by;
+                            sum[kSaxbx] = fma(ax, bx, sum[kSaxbx]); sum[kSaxby] = fma(ax, by, sum[kSaxby]);
+                            sum[kSaybx] = fma(ay, bx, sum[kSaybx]); sum[kSayby] = fma(ay, by, sum[kSayby]);
                             const double ex = Px - q.x, ey = Py - q.y;
-                            sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+                            sum[kSerr] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
                         }
                     }
                     const int rt = tile * SUBT + sub;                           // reduction tile
                     if (rt < ntiles) {                                       // warp-uniform
-                        const double (&s8)[8] = reinterpret_cast<const double (&)[8]>(sum);
-                        const double tot = warp_sum8(s8, lane);              // sums 0..7, see warp_sum8
-                        const double e8 = warp_sum(sum[8]);
+                        const double tot = warp_sum8(sum, lane);             // lane L: total of column id(L), see warp_sum8
                         if ((lane & 3) == 0)
                             redp[rt * kNumSums + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
-                        if (lane == 1) redp[rt * kNumSums + 8] = e8;
+                        imin = __reduce_min_sync(0xffffffffu, imin); imax = __reduce_max_sync(0xffffffffu, imax);
+                        if (lane == 0) mmp[rt] = make_int2(imin, imax);
                     }
                     }
                 }
@@ -635,24 +782,31 @@ icp_align_kernel(const KernelArgs a)
             sync_all();
             if (tid == 0) s_tile_ctr[passes & 1] = 0;          // next used two passes from now
             // every warp folds the tile partials in the same fixed order and updates its own copy of T:
-            // lane k + 9*part (part 0..2) adds column k over tiles = part (mod 3), in tile order
+            // lane k + 8*part (part 0..3) adds column k over tiles = part (mod 4), in tile order; two
+            // butterfly levels add the four parts, then column k is broadcast from lane k
             double S[kNumSums];
+            bool single_target;                                // every source point matched the same target
             {
                 double col = 0.0;
-                if (lane < 3 * kNumSums) {
-                    const int k = lane % kNumSums;
-                    if (!CLUSTER) {
-                        for (int t = lane / kNumSums; t < ntiles; t += 3) col += redp[t * kNumSums + k];
-                    } else {                                     // tile t lives in CTA t mod csize
-                        cg::cluster_group cluster = cg::this_cluster();
-                        for (int t = lane / kNumSums; t < ntiles; t += 3)
-                            col += cluster.map_shared_rank(redp, (t / SUBT) % csize)[t * kNumSums + k];
+                const int k = lane & 7;
+                int mn = 0x7fffffff, mx = -1;
+                if (!CLUSTER) {
+                    for (int t = lane >> 3; t < ntiles; t += 4) col += redp[t * kNumSums + k];
+                    for (int t = lane; t < ntiles; t += 32) { const int2 v = mmp[t]; mn = min(mn, v.x); mx = max(mx, v.y); }
+                } else {                                     // tile t lives in CTA (t / SUBT) mod csize
+                    cg::cluster_group cluster = cg::this_cluster();
+                    for (int t = lane >> 3; t < ntiles; t += 4)
+                        col += cluster.map_shared_rank(redp, (t / SUBT) % csize)[t * kNumSums + k];
+                    for (int t = lane; t < ntiles; t += 32) {
+                        const int2 v = cluster.map_shared_rank(mmp, (t / SUBT) % csize)[t];
+                        mn = min(mn, v.x); mx = max(mx, v.y);
                     }
                 }
+                single_target = __reduce_min_sync(0xffffffffu, mn) == __reduce_max_sync(0xffffffffu, mx);
+                col += __shfl_xor_sync(0xffffffffu, col, 8);
+                col += __shfl_xor_sync(0xffffffffu, col, 16);
 #pragma unroll
-                for (int k = 0; k < kNumSums; ++k)
-                    S[k] = (__shfl_sync(0xffffffffu, col, k) + __shfl_sync(0xffffffffu, col, k + kNumSums))
-                           + __shfl_sync(0xffffffffu, col, k + 2 * kNumSums);
+                for (int kk = 0; kk < 7; ++kk) S[kk] = __shfl_sync(0xffffffffu, col, kk);
             }
             {
                 double T[6];
@@ -660,15 +814,22 @@ icp_align_kernel(const KernelArgs a)
                 for (int k = 0; k < 6; ++k) T[k] = Tmine[k];
                 double cx, cy;
                 apply_T(T, s0.x, s0.y, cx, cy);
-                const double ma_x = S[0] * inv_n, ma_y = S[1] * inv_n, mb_x = S[2] * inv_n, mb_y = S[3] * inv_n;
+                // sum of the moved source points minus c: the linear part of T applied to S0
+                const double Sax = fma(T[1], S0[1], T[0] * S0[0]), Say = fma(T[4], S0[1], T[3] * S0[0]);
+                const double ma_x = Sax * inv_n, ma_y = Say * inv_n, mb_x = S[kSbx] * inv_n, mb_y = S[kSby] * inv_n;
                 // centred cross-covariance S = X Y^T (src/icp.py:29-32)
-                const double s00 = S[4] - S[0] * mb_x, s01 = S[5] - S[0] * mb_y;
-                const double s10 = S[6] - S[1] * mb_x, s11 = S[7] - S[1] * mb_y;
+                const double s00 = S[kSaxbx] - Sax * mb_x, s01 = S[kSaxby] - Sax * mb_y;
+                const double s10 = S[kSaybx] - Say * mb_x, s11 = S[kSayby] - Say * mb_y;
                 // rotation maximising tr(R S): closed form of the SVD + det fix (src/icp.py:33-38)
                 const double A = s00 + s11, Bv = s01 - s10;
                 const double h2 = A * A + Bv * Bv;
+                // One distinct matched target: the centred target cloud is zero, the covariance is zero and
+                // its SVD gives the identity rotation (SURVEY probe B5).  The reference only gets there when
+                // its mean of N copies happens to round to the value itself; otherwise its rotation is the
+                // rounding noise of that mean.  Here the case is decided exactly: identity.
                 double c = 1.0, s = 0.0;
-                if (h2 > 0.0 && h2 < 1e300) {
+                if (single_target) {
+                } else if (h2 > 0.0 && h2 < 1e300) {
                     const double rh = rsqrt(h2);
                     c = A * rh; s = Bv * rh;
                 } else if (h2 > 0.0) {                                   // huge coordinates: scale first
@@ -689,11 +850,12 @@ icp_align_kernel(const KernelArgs a)
                 N[3] = s * T[0] + c * T[3];
                 N[4] = s * T[1] + c * T[4];
                 N[5] = s * T[2] + c * T[5] + ty;
-                err = S[8];
+                err = S[kSerr];
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) Tmine[k] = N[k];
+                    Tmine[6] = stretch_of(N);
                     if (warp == 0 && crank == 0 && a.hist && passes < a.p.hist_cap) {
                         double *hrow = a.hist + ((size_t)pid * a.p.hist_cap + passes) * 6;
 #pragma unroll
@@ -717,13 +879,33 @@ icp_align_kernel(const KernelArgs a)
             a.err_out[pid] = err;
             a.passes_out[pid] = passes;
         }
-        if (a.n_peers > 0 && crank == 0 && tid < 8 * a.n_peers) {
-            const int r = tid >> 3, k = tid & 7;                // 8 lanes per peer: one 64-byte record each
-            // every warp reads its OWN copy of T (identical bits, ordered by its own __syncwarp):
-            // with more than four peers the lanes of warp 1 store too, and warp 0's copy is not
-            // ordered against them
-            const double v = k < 6 ? Tmine[k] : (k == 6 ? err : (double)passes);
-            a.peers[r][(a.rec_row0 + pid) * 8 + k] = v;
+        // ---- epilogues: constraint records straight into the consumers' buffers ----
+        if ((a.n_peers > 0 || a.accept_rec || a.accept_peers) && crank == 0) {
+            const int64_t row = a.rec_row0 + (pid / a.rec_block) * a.rec_stride + pid % a.rec_block;
+            // every warp reads its OWN copy of T (identical bits, ordered by its own __syncwarp)
+            auto field = [&](int k) -> double {
+                return k < 6 ? Tmine[k] : (k == 6 ? err : (double)passes);
+            };
+            if (a.peers)                                         // fused all-gather: one 64-byte record per peer
+                for (int t = tid; t < 8 * a.n_peers; t += NT)
+                    a.peers[t >> 3][row * 8 + (t & 7)] = field(t & 7);
+            if ((a.accept_rec || a.accept_peers) && err < a.accept_thresh && warp == 0) {
+                // acceptance test + compaction (src/loop_closure_detection.py:35-39): append in
+                // completion order; the row id travels in the record, so the consumer can restore order
+                long long slot = 0;
+                if (lane == 0) slot = (long long)atomicAdd(a.accept_ctr, 1ULL);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot < a.accept_cap) {
+                    const long long tag = (long long)((row << 16) | (int64_t)min(passes, 0xffff));
+                    const int npeer = a.accept_peers ? a.n_peers : 1;
+                    for (int t = lane; t < 8 * npeer; t += 32) {
+                        const int k = t & 7;
+                        double *base = a.accept_peers ? a.accept_peers[t >> 3] + (size_t)a.accept_rank * a.accept_cap * 8
+                                                      : a.accept_rec;
+                        base[slot * 8 + k] = k == 7 ? __longlong_as_double(tag) : field(k);
+                    }
+                }
+            }
         }
         if (a.corr) {
             int32_t *crow = a.corr + (size_t)pid * a.p.corr_stride;
@@ -738,20 +920,36 @@ icp_align_kernel(const KernelArgs a)
         const unsigned long long ex = (unsigned long long)executed * (unsigned long long)(kChunk * 32 * R);
         if (lane == 0 && ex) atomicAdd(a.executed, ex);
     }
+    if ((a.accept_rec || a.accept_peers) && tid == 0 && crank == 0) {
+        // the last CTA (cluster) to leave publishes how many records were appended
+        __threadfence();
+        const unsigned long long left = atomicAdd(a.accept_ctr + 1, 1ULL) + 1;
+        const unsigned long long total_ctas = (unsigned long long)(gridDim.x / csize);
+        if (left == total_ctas) {
+            __threadfence();
+            long long n = (long long)*(volatile unsigned long long *)a.accept_ctr;
+            if (n > a.accept_cap) n = -n;                        // overflow: the caller sees a negative count
+            if (a.accept_count_peers)
+                for (int r = 0; r < a.n_peers; ++r) a.accept_count_peers[r][a.accept_rank] = n;
+            else if (a.accept_count_out)
+                *a.accept_count_out = n;
+        }
+    }
 }
 
 
 // Rigid fit of n matched point pairs a[i] -> b[i] and their SSE: the reference's get_transform
 // (src/icp.py:22-46) and get_error (src/icp.py:49-52) as stand-alone operations.  One CTA.
+constexpr int kFitSums = 9;
 __global__ void __launch_bounds__(256)
 fit_pairs_kernel(const double2 *a, const double2 *b, int n, double *T_out, double *err_out)
 {
-    __shared__ double red[8][kNumSums];
+    __shared__ double red[8][kFitSums];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double2 a0 = a[0], b0 = b[0];
-    double sum[kNumSums];
+    double sum[kFitSums];
 #pragma unroll
-    for (int k = 0; k < kNumSums; ++k) sum[k] = 0.0;
+    for (int k = 0; k < kFitSums; ++k) sum[k] = 0.0;
     for (int i = tid; i < n; i += blockDim.x) {
         const double2 p = a[i], q = b[i];
         const double ax = p.x - a0.x, ay = p.y - a0.y, bx = q.x - b0.x, by = q.y - b0.y;
@@ -762,15 +960,15 @@ fit_pairs_kernel(const double2 *a, const double2 *b, int n, double *T_out, doubl
         sum[8] += __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
     }
 #pragma unroll
-    for (int k = 0; k < kNumSums; ++k) sum[k] = warp_sum(sum[k]);
+    for (int k = 0; k < kFitSums; ++k) sum[k] = warp_sum(sum[k]);
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < kNumSums; ++k) red[warp][k] = sum[k];
+        for (int k = 0; k < kFitSums; ++k) red[warp][k] = sum[k];
     }
     __syncthreads();
     if (tid == 0) {
-        double S[kNumSums];
-        for (int k = 0; k < kNumSums; ++k) {
+        double S[kFitSums];
+        for (int k = 0; k < kFitSums; ++k) {
             S[k] = 0.0;
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) S[k] += red[w][k];
         }

@@ -28,7 +28,7 @@ from ._lib import IcpbError  # noqa: F401  (re-exported)
 
 __all__ = ["icp", "icp_iteration", "icp_batch", "get_correspondences", "get_closest_point",
            "get_transform", "get_error",
-           "ScanTable", "IcpEngine", "BatchResult", "engine"]
+           "ScanTable", "ScanList", "IcpEngine", "BatchResult", "engine", "make_epilogue"]
 
 
 # --------------------------------------------------------------------------- scan table
@@ -59,6 +59,15 @@ class ScanTable:
                 raise ValueError("offsets must start at 0, end at len(xy) and be strictly increasing")
         if not np.isfinite(self.xy).all():
             raise ValueError("scan table holds non-finite coordinates")
+
+    @classmethod
+    def from_lengths(cls, lengths) -> "ScanTable":
+        """A table known only by its scan lengths (the scans themselves live in device memory, uploaded
+        from a list of arrays): enough for index validation and result shapes."""
+        t = cls.__new__(cls)
+        t.xy = None
+        t.offsets = np.concatenate(([0], np.cumsum(np.asarray(lengths, dtype=np.int64)))).astype(np.int64)
+        return t
 
     @property
     def n_scans(self) -> int:
@@ -117,6 +126,59 @@ def _ptr(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
+class ScanList:
+    """The reference's ``lidar_points`` as it is -- a sequence of separate (m_i, 2) float64 arrays in
+    pageable memory (src/dataloader.py:110-112) -- described by a pointer and a length per scan for
+    ``icpb_align_host_scans``.  Nothing is copied unless an element is not a C-ordered float64 array;
+    the library packs and checks the coordinates itself, overlapped with the upload."""
+
+    def __init__(self, scans):
+        n = len(scans)
+        if n == 0:
+            raise ValueError("empty scan list")
+        self.ptrs = np.empty(n, dtype=np.uint64)
+        self.lens = np.empty(n, dtype=np.int64)
+        self.keep = scans                      # the arrays must outlive the call
+        helper = _lib.pyhelper()
+        k = helper.icpb_py_scan_ptrs(scans, _ptr(self.ptrs), _ptr(self.lens), n) if helper else 0
+        if k < 0:
+            k = 0
+        if k < n:                              # elements the helper did not take: convert them one by one
+            fixed = list(scans[:k]) if k else []
+            for i in range(k, n):
+                a = np.ascontiguousarray(scans[i], dtype=np.float64)
+                if a.ndim != 2 or a.shape[1] != 2:
+                    raise ValueError(f"scan {i} has shape {a.shape}; expected (m, 2) as get_point_cloud returns")
+                fixed.append(a)
+                self.ptrs[i] = a.ctypes.data
+                self.lens[i] = a.shape[0]
+            self.keep = fixed
+        if (self.lens <= 0).any():
+            bad = int(np.argmax(self.lens <= 0))
+            raise ValueError(f"scan {bad} is empty (the reference's argmin raises on an empty cloud)")
+
+    @property
+    def n_scans(self) -> int:
+        return len(self.lens)
+
+
+def make_epilogue(peer_ptrs_dev=0, n_peers=0, rank=0, row0=0, row_block=0, row_stride=0,
+                  accept_thresh=None, accept_rec=0, accept_count=0, accept_peer_ptrs=0,
+                  accept_count_peer_ptrs=0, accept_cap=0) -> _lib.IcpbEpilogue:
+    """icpb_epilogue from raw device addresses (ints; 0 = not used).  See include/icpb.h."""
+    ep = _lib.IcpbEpilogue()
+    ep.d_peer_ptrs = int(peer_ptrs_dev) or None
+    ep.n_peers, ep.rank = int(n_peers), int(rank)
+    ep.row0, ep.row_block, ep.row_stride = int(row0), int(row_block), int(row_stride)
+    ep.accept_thresh = float(accept_thresh) if accept_thresh is not None else 0.0
+    ep.d_accept_rec = int(accept_rec) or None
+    ep.d_accept_count = int(accept_count) or None
+    ep.d_accept_peer_ptrs = int(accept_peer_ptrs) or None
+    ep.d_accept_count_peer_ptrs = int(accept_count_peer_ptrs) or None
+    ep.accept_cap = int(accept_cap)
+    return ep
+
+
 def _params(epsilon, max_iters, stopping_thresh, rotation_only, exhaustive=False) -> _lib.IcpbParams:
     p = _lib.default_params()
     p.flags = _lib.FLAG_EXHAUSTIVE if exhaustive else 0
@@ -137,16 +199,20 @@ def max_passes(max_iters: int) -> int:
 
 
 # --------------------------------------------------------------------------- engine
+def resolve_device(device: int | None) -> int:
+    """None -> ICPB_DEVICE, else LOCAL_RANK (one process per GPU), else 0."""
+    if device is None:
+        device = os.environ.get("ICPB_DEVICE", os.environ.get("LOCAL_RANK", "0"))
+    return int(device)
+
+
 class IcpEngine:
     """One icpb handle: per process and per device (the replacement for a loky worker)."""
 
     def __init__(self, device: int | None = None):
         self._h = ctypes.c_void_p()
         self._L = _lib.lib()
-        if device is None:
-            device = int(os.environ.get("LOCAL_RANK", "0")) if "ICPB_DEVICE" not in os.environ \
-                else int(os.environ["ICPB_DEVICE"])
-        self.device = int(device)
+        self.device = resolve_device(device)
         _lib.check(self._L.icpb_create(self.device, ctypes.byref(self._h)), "icpb_create")
         self.table: ScanTable | None = None
         self._keep = None
@@ -161,6 +227,10 @@ class IcpEngine:
             self.close()
         except Exception:
             pass
+
+    def set_tuning(self, key: str, value: int):
+        """Per-handle tuning / test hook (icpb_set_tuning; nothing is read from the environment)."""
+        _lib.check(self._L.icpb_set_tuning(self._h, key.encode(), int(value)), "icpb_set_tuning")
 
     # -- scan table -----------------------------------------------------------------------
     def set_scans(self, scans) -> ScanTable:
@@ -232,10 +302,12 @@ class IcpEngine:
 
     # -- upload + run in one call, upload overlapped with the kernels ---------------------------
     def align(self, scans, pairs, init_transforms=None, epsilon=0.01, max_iters=100, stopping_thresh=0.0001,
-              rotation_only=False, exhaustive: bool = False) -> BatchResult:
-        """`set_scans` + `run` through icpb_align_host: the scan table is copied in segments and
-        every pair starts as soon as both of its scans are on the device."""
-        table = scans if isinstance(scans, ScanTable) else ScanTable(scans)
+              rotation_only=False, exhaustive: bool = False, epilogue: _lib.IcpbEpilogue | None = None) -> BatchResult:
+        """Upload + run in one call (icpb_align_host_ex / icpb_align_host_scans): the scan table goes up
+        in pieces and every pair starts as soon as both of its scans are on the device.  ``scans`` is a
+        ScanTable (packed, ideally pinned) or the reference's own list of (m_i, 2) arrays, which the
+        library packs into pinned staging with a few host threads while earlier pieces are on the wire.
+        ``epilogue``: fused all-gather / acceptance of the records (multi-GPU, see dist.FusedGather)."""
         p = _params(epsilon, max_iters, stopping_thresh, rotation_only, exhaustive)
         pairs_a = np.ascontiguousarray(pairs, dtype=np.int32)
         if pairs_a.size == 0:
@@ -254,12 +326,35 @@ class IcpEngine:
         T33 = np.empty((B, 3, 3))
         err = np.empty(B)
         passes = np.empty(B, dtype=np.int32)
-        _lib.check(self._L.icpb_align_host_ld(self._h, _ptr(table.xy), _ptr(table.offsets), table.n_scans,
-                                              _ptr(pairs_a), _ptr(init33), 9, B, ctypes.byref(p),
-                                              _ptr(T33), 9, _ptr(err), _ptr(passes)), "icpb_align_host")
-        self.table = table
-        self._keep = None
+        ep = ctypes.byref(epilogue) if epilogue is not None else None
+        prev, self.table = (self.table, self._keep), None
+        try:
+            table = self._align_call(scans, pairs_a, init33, B, p, T33, err, passes, ep)
+        except Exception:
+            # rejected before anything was touched (bad pairs / guesses): the old table is still there;
+            # failed part-way: the library has dropped it (icpb_scan_count == 0)
+            if self._L.icpb_scan_count(self._h) > 0:
+                self.table, self._keep = prev
+            raise
+        self.table, self._keep = table, None
         return BatchResult(T33, err, passes, None, None)
+
+    def _align_call(self, scans, pairs_a, init33, B, p, T33, err, passes, ep):
+        if isinstance(scans, ScanTable):
+            table = scans
+            if table.xy is None:
+                raise ValueError("this ScanTable only describes a resident table; pass the scans themselves")
+            _lib.check(self._L.icpb_align_host_ex(self._h, _ptr(table.xy), _ptr(table.offsets), table.n_scans,
+                                                  _ptr(pairs_a), _ptr(init33), 9, B, ctypes.byref(p),
+                                                  _ptr(T33), 9, _ptr(err), _ptr(passes), ep), "icpb_align_host")
+        else:
+            sl = scans if isinstance(scans, ScanList) else ScanList(scans)
+            _lib.check(self._L.icpb_align_host_scans(self._h, _ptr(sl.ptrs), _ptr(sl.lens), sl.n_scans,
+                                                     _ptr(pairs_a), _ptr(init33), 9, B, ctypes.byref(p),
+                                                     _ptr(T33), 9, _ptr(err), _ptr(passes), ep),
+                       "icpb_align_host_scans")
+            table = ScanTable.from_lengths(sl.lens)
+        return table
 
     # -- device-buffer run (inputs and outputs resident in HBM; torch tensors) ---------------
     def run_device(self, pairs_t, init_t, out_T, out_err, out_passes, epsilon=0.01, max_iters=100,
@@ -290,6 +385,29 @@ class IcpEngine:
                                            vp(out_passes.data_ptr()), None, None, vp(stream)),
                    "icpb_run_device")
 
+    def run_device_ex(self, pairs_t, init_t, out_T, out_err, out_passes, epilogue: _lib.IcpbEpilogue | None,
+                      epsilon=0.01, max_iters=100, stopping_thresh=0.0001, rotation_only=False,
+                      all_pairs: tuple | None = None, stream=None):
+        """`run_device` with kernel epilogues (icpb_run_device_ex): the fused all-gather of the
+        constraint records into every rank's buffer and/or the acceptance test + compaction."""
+        import torch
+        p = _params(epsilon, max_iters, stopping_thresh, rotation_only)
+        if all_pairs is not None:
+            p.pair_mode = 1
+            p.k_first, p.k_block, p.k_stride, B = (int(v) for v in all_pairs)
+        else:
+            B = int(pairs_t.shape[0])
+            p.k_block = max(B, 1)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        vp = ctypes.c_void_p
+        _lib.check(self._L.icpb_run_device_ex(self._h, vp(pairs_t.data_ptr()) if all_pairs is None else None,
+                                              vp(init_t.data_ptr()) if init_t is not None else None, B,
+                                              ctypes.byref(p), vp(out_T.data_ptr()), vp(out_err.data_ptr()),
+                                              vp(out_passes.data_ptr()),
+                                              ctypes.byref(epilogue) if epilogue is not None else None, vp(stream)),
+                   "icpb_run_device_ex")
+
     def run_device_gather(self, pairs_t, init_t, out_T, out_err, out_passes, peer_ptrs_dev: int, n_peers: int,
                           row0: int, epsilon=0.01, max_iters=100, stopping_thresh=0.0001, rotation_only=False,
                           stream=None):
@@ -297,18 +415,9 @@ class IcpEngine:
         [T(6), error, passes] is stored into every rank's (total, 8) float64 gather buffer at row
         row0 + pair id over NVLink peer memory.  `peer_ptrs_dev` is the device address of the array
         of peer buffer pointers (torch symmetric memory: ``handle.buffer_ptrs_dev``)."""
-        import torch
-        p = _params(epsilon, max_iters, stopping_thresh, rotation_only)
-        B = int(pairs_t.shape[0])
-        p.k_block = max(B, 1)
-        if stream is None:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-        vp = ctypes.c_void_p
-        _lib.check(self._L.icpb_run_device_gather(self._h, vp(pairs_t.data_ptr()),
-                                                  vp(init_t.data_ptr()) if init_t is not None else None, B,
-                                                  ctypes.byref(p), vp(out_T.data_ptr()), vp(out_err.data_ptr()),
-                                                  vp(out_passes.data_ptr()), vp(int(peer_ptrs_dev)), int(n_peers),
-                                                  int(row0), vp(stream)), "icpb_run_device_gather")
+        ep = make_epilogue(peer_ptrs_dev, n_peers, row0=row0)
+        self.run_device_ex(pairs_t, init_t, out_T, out_err, out_passes, ep, epsilon, max_iters, stopping_thresh,
+                           rotation_only, stream=stream)
 
     # -- one pair given as two arrays ------------------------------------------------------------
     def pair(self, src_xy, dst_xy, init6, p: _lib.IcpbParams, want_hist: bool, want_corr: bool):
@@ -353,6 +462,7 @@ _engines: dict = {}
 def engine(device: int | None = None) -> IcpEngine:
     """Lazily created per (process, device): safe to call from loky/fork workers because the
     handle is keyed by pid and created on first use in that process."""
+    device = resolve_device(device)                    # engine(None) and engine(0) share one handle
     key = (os.getpid(), device)
     e = _engines.get(key)
     if e is None:

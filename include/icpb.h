@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ICPB_ABI_VERSION 1
+#define ICPB_ABI_VERSION 2
 
 #define ICPB_EINVAL   10001   /* bad argument (null pointer, empty scan, negative size ...)   */
 #define ICPB_ETOOLONG 10002   /* a scan does not fit the kernel's shared-memory staging       */
@@ -101,7 +101,7 @@ int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init,
 
 /*
  * Multi-GPU: icpb_run_device with the gather of the constraint records fused into the kernel.
- * d_peer_ptrs is a device array of n_peers (<= 8) pointers: the gather buffer of every rank
+ * d_peer_ptrs is a device array of n_peers pointers: the gather buffer of every rank
  * ((total pairs, 8) float64 rows [T(6), error, passes]) as mapped into THIS process (CUDA peer /
  * symmetric memory).  Each finished pair stores its record into every buffer at row
  * row0 + pair id, over NVLink, instead of a separate all-gather after the kernel.  The caller
@@ -111,6 +111,51 @@ int icpb_run_device(icpb_handle h, const int32_t *d_pairs, const double *d_init,
 int icpb_run_device_gather(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
                            const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
                            const uint64_t *d_peer_ptrs, int32_t n_peers, int64_t row0, void *stream);
+
+/*
+ * What the alignment kernel does with a finished pair besides writing d_T / d_err / d_passes: the
+ * exchange step of the multi-GPU path and the acceptance test of the loop-closure callers, as kernel
+ * epilogues.  All pointers are device pointers; zero-initialise the struct and fill what is wanted.
+ *
+ * Fused all-gather (d_peer_ptrs != NULL): the pair's 64-byte record [T(6), error, passes] (8 float64)
+ *   is stored into EVERY rank's gather buffer -- d_peer_ptrs is a device array of n_peers addresses,
+ *   each rank's (total pairs, 8) float64 buffer as mapped into this process (CUDA peer / symmetric
+ *   memory) -- at row  row0 + (b / row_block) * row_stride + b % row_block  for local problem b
+ *   (row_block <= 0: rows row0 .. row0 + B - 1).  With row0 = rank * block, row_block = block,
+ *   row_stride = world * block this is the interleaved-block partition of the problem index space
+ *   (SURVEY.md section 8e), so every rank ends up with all records in global problem order and no
+ *   collective runs after the kernel; the caller orders the launch before a cross-rank barrier.
+ *   Replaces the result gather of the reference's fan-out, `zip(*parallel(...))`
+ *   (scripts/main.py:241), across ranks.
+ *
+ * Acceptance + compaction (d_accept_rec or d_accept_peer_ptrs != NULL): pairs whose error is below
+ *   accept_thresh -- the reference's `if error < err_thresh: add_constraint(...)`
+ *   (src/loop_closure_detection.py:35-39, 155-159) -- append [T(6), error, tag] with the int64 tag
+ *   (row << 16) | min(passes, 65535) stored in the 8th slot's bits, in completion order, so only
+ *   accepted constraints cross PCIe / NVLink.  Single GPU: into d_accept_rec (accept_cap rows), the
+ *   number of rows into *d_accept_count when the launch completes.  Multi-GPU: into region `rank`
+ *   (rows rank * accept_cap ...) of every peer's buffer d_accept_peer_ptrs[r], the count into slot
+ *   `rank` of every peer's int64 array d_accept_count_peer_ptrs[r].  A count above accept_cap is
+ *   reported negated (the buffer then holds the first accept_cap rows).  The consumer restores the
+ *   reference's order by sorting on the row in the tag.
+ */
+typedef struct icpb_epilogue {
+    const uint64_t *d_peer_ptrs;
+    int32_t  n_peers;
+    int32_t  rank;
+    int64_t  row0, row_block, row_stride;
+    double   accept_thresh;
+    double  *d_accept_rec;
+    int64_t *d_accept_count;
+    const uint64_t *d_accept_peer_ptrs;
+    const uint64_t *d_accept_count_peer_ptrs;
+    int64_t  accept_cap;
+} icpb_epilogue;
+
+/* icpb_run_device with epilogues (ep may be NULL); no history / correspondences. */
+int icpb_run_device_ex(icpb_handle h, const int32_t *d_pairs, const double *d_init, int64_t B,
+                       const icpb_params *p, double *d_T, double *d_err, int32_t *d_passes,
+                       const icpb_epilogue *ep, void *stream);
 
 /* Same with host buffers: copies the inputs to the device, runs, copies the results back and
  * synchronises.  This is the call a reference-side binding makes. */
@@ -142,6 +187,24 @@ int icpb_plan_upload(const int64_t *h_offsets, int64_t n_scans, int32_t pieces_w
 int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
                        const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
                        const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes);
+
+/* icpb_align_host_ld with epilogues: on a multi-GPU run the records go from the kernel straight into
+ * every rank's gather buffer while this rank's own results still come back to h_T / h_err / h_passes. */
+int icpb_align_host_ex(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
+                       const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                       const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
+                       const icpb_epilogue *ep);
+
+/* The same with the scans exactly as the reference holds them: `lidar_points`, a list of n_scans
+ * separate (m_i, 2) float64 C-ordered arrays in ordinary pageable memory (src/dataloader.py:110-112,
+ * the arguments of scripts/main.py:242-243).  scan_xy[s] points at scan s, scan_len[s] = m_i.  A few
+ * host threads copy the scans into a pinned staging table piece by piece (checking for non-finite
+ * coordinates on the way: ICPB_EINVAL) while earlier pieces are already on their way to the device and
+ * the kernel is aligning the pairs whose scans have landed. */
+int icpb_align_host_scans(icpb_handle h, const double *const *scan_xy, const int64_t *scan_len, int64_t n_scans,
+                          const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                          const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
+                          const icpb_epilogue *ep);
 
 /* One pair given directly as two (n, 2) float64 host arrays: the reference's
  * icp(pc1, pc2, init_transform, epsilon, max_iters, stopping_thresh, rotation_only)
@@ -227,8 +290,19 @@ typedef struct icpb_kernel_info {
 } icpb_kernel_info;
 int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out);
 
+/* Tuning and test hooks, per handle (nothing is read from the environment).  Keys: "threads" (CTA
+ * width cap, multiple of 32), "cluster" (force a cluster size: 0/1 never, 2/4/8), "segments" (upload
+ * pieces), "pack_threads" (host threads of icpb_align_host_scans, default min(8, cpus)),
+ * "sgd_cluster", "flag_copy" (arrival counter by 4-byte copies), "drop_counter" (tests: never
+ * advance the arrival counter), "trace" (host timings on stderr).  0 / -1 restore the default. */
+int icpb_set_tuning(icpb_handle h, const char *key, int64_t value);
+
 /* Number of alignment-kernel launches made through this handle (bench.py's gpu_launches). */
 int64_t icpb_launch_count(icpb_handle h);
+
+/* Scans of the table resident on the handle's device, 0 when there is none (never set, or an
+ * icpb_align_host* call failed part-way and left the buffer half written). */
+int64_t icpb_scan_count(icpb_handle h);
 
 /* Optional instrumentation: while enabled, launches add the point-pair distance evaluations
  * they actually execute (after pruning) to a device counter; icpb_read_work synchronises the

@@ -336,7 +336,7 @@ def test_align_in_order_batch_and_bad_inputs(gicp):
     e.close()
 
 
-def test_align_survives_a_missing_arrival_counter(gicp, monkeypatch):
+def test_align_survives_a_missing_arrival_counter(gicp):
     """If the 'piece k has arrived' counter never moves (a profiler serialising the kernel against the
     copy stream, a failed transfer), the waiting CTAs give up after ~0.5 s, flag it, and the library
     reruns the batch on the by then resident table: same results, no hang."""
@@ -344,9 +344,9 @@ def test_align_survives_a_missing_arrival_counter(gicp, monkeypatch):
     scans, pairs, init, _, _ = synth.make_chain_workload(120, 360, seed=6)
     e = gicp.IcpEngine()
     ref = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
-    monkeypatch.setenv("ICPB_TEST_DROP_COUNTER", "1")
+    e.set_tuning("drop_counter", 1)
     got = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
-    monkeypatch.delenv("ICPB_TEST_DROP_COUNTER")
+    e.set_tuning("drop_counter", 0)
     np.testing.assert_array_equal(got.T, ref.T)
     np.testing.assert_array_equal(got.iters, ref.iters)
     e.close()
@@ -376,7 +376,6 @@ def test_helper_functions(gicp, c_oracle):
 def test_cluster_latency_mode_bit_identical(gicp, n_beams, cluster):
     """Latency mode: one thread-block cluster per pair, tiles dealt to the CTAs, partial sums folded
     over distributed shared memory in the same order -> the same bits as the single-CTA kernel."""
-    import os
     from icp_slam_b200 import synth
     rng = np.random.default_rng(n_beams + cluster)
     poses = synth.loop_trajectory(6, step=0.08)
@@ -384,19 +383,12 @@ def test_cluster_latency_mode_bit_identical(gicp, n_beams, cluster):
     pairs = np.array([(1, 0), (2, 1), (5, 2), (3, 3)], dtype=np.int32)
     e = gicp.IcpEngine()
     e.set_scans(scans)
-    old = os.environ.get("ICPB_CLUSTER")
-    try:
-        os.environ["ICPB_CLUSTER"] = "0"
-        a = e.run(pairs, None, epsilon=0.05, max_iters=100, return_history=True, return_correspondences=True)
-        os.environ["ICPB_CLUSTER"] = str(cluster)
-        b = e.run(pairs, None, epsilon=0.05, max_iters=100, return_history=True, return_correspondences=True)
-        os.environ.pop("ICPB_CLUSTER")
-        c = e.run(pairs[:1], None, epsilon=0.05, max_iters=100)          # automatic choice for one pair
-    finally:
-        if old is None:
-            os.environ.pop("ICPB_CLUSTER", None)
-        else:
-            os.environ["ICPB_CLUSTER"] = old
+    e.set_tuning("cluster", 0)
+    a = e.run(pairs, None, epsilon=0.05, max_iters=100, return_history=True, return_correspondences=True)
+    e.set_tuning("cluster", cluster)
+    b = e.run(pairs, None, epsilon=0.05, max_iters=100, return_history=True, return_correspondences=True)
+    e.set_tuning("cluster", -1)
+    c = e.run(pairs[:1], None, epsilon=0.05, max_iters=100)          # automatic choice for one pair
     np.testing.assert_array_equal(a.T, b.T)
     np.testing.assert_array_equal(a.error, b.error)
     np.testing.assert_array_equal(a.iters, b.iters)

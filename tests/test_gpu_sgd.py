@@ -103,19 +103,24 @@ def test_random_graphs_against_the_oracle(n, n_loops, seed):
     np.testing.assert_allclose(pg.poses, want, **TOL)
 
 
-def test_cluster_sizes_give_the_same_bits(monkeypatch):
+def test_cluster_sizes_give_the_same_bits():
     """The poses of one graph held by 1, 2, 4 and 8 CTAs: same arithmetic, same bits."""
     from icp_slam_b200 import pose_graph_optimization as pgo
     z = sgd_golden()
     ab = z["edges"].astype(np.int32)
     T6 = z["edge_T"][:, :2, :].reshape(-1, 6)
     keep = ab[:, 1] > ab[:, 0] + 1
-    monkeypatch.delenv("ICPB_SGD_CLUSTER", raising=False)
+    from icp_slam_b200 import icp as gicp
+    eng = gicp.engine()
+    eng.set_tuning("sgd_cluster", 0)
     one = pgo.sgd_steps(z["poses0"], ab[keep], T6[keep], [1.0, 0.5])
-    for size in (2, 4, 8):
-        monkeypatch.setenv("ICPB_SGD_CLUSTER", str(size))
-        got = pgo.sgd_steps(z["poses0"], ab[keep], T6[keep], [1.0, 0.5])
-        np.testing.assert_array_equal(got, one)
+    try:
+        for size in (2, 4, 8):
+            eng.set_tuning("sgd_cluster", size)
+            got = pgo.sgd_steps(z["poses0"], ab[keep], T6[keep], [1.0, 0.5])
+            np.testing.assert_array_equal(got, one)
+    finally:
+        eng.set_tuning("sgd_cluster", 0)
     np.testing.assert_allclose(one, z["poses_after"][1], **TOL)
 
 

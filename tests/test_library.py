@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, s), s
     assert sorted(_lib.EXPORTS) == syms
     L.icpb_abi_version.restype = ctypes.c_int
-    assert L.icpb_abi_version() == 1
+    assert L.icpb_abi_version() == 2
 
 
 def test_default_params_match_reference_defaults():

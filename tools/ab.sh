@@ -1,9 +1,11 @@
 #!/bin/bash
-# A/B runs of bench.py's device leg under different tuning environments (developer tool).
-#   bash tools/ab.sh name1:ENV=VAL,ENV2=VAL name2: ...
-for spec in "$@"; do
-  name=${spec%%:*}; envs=${spec#*:}
-  env $(echo $envs | tr ',' ' ') python bench.py --no-e2e --steps 10 --warmup 3 > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+# A/B runs of bench.py's device leg under different library builds (developer tool).
+#   bash tools/ab.sh name1 name2 ...     (names of tools/build_variant.sh builds; "base" = libicpb.so)
+#   AB_ARGS="--workload chain --beams 360" bash tools/ab.sh ...
+for name in "$@"; do
+  so=icp-slam-with-loop-closure_b200/libicpb_${name}.so
+  [ "$name" = base ] && so=icp-slam-with-loop-closure_b200/libicpb.so
+  ICPB_SO=$PWD/$so python bench.py --no-e2e --no-cpu --steps 10 --warmup 3 $AB_ARGS > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
   python - "$name" <<PY
 import json, sys
 f = sys.argv[1]

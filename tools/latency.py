@@ -11,15 +11,13 @@ for beams in (360, 1024, 4096):
     p1, p2 = hom(scans[1]), hom(scans[0])
     e = gicp.IcpEngine(0); e.set_scans(scans)
     pairs = np.array([[1, 0]], dtype=np.int32)
-    for cl in ("0", "2", "4", "8", None):
-        if cl is None: os.environ.pop("ICPB_CLUSTER", None)
-        else: os.environ["ICPB_CLUSTER"] = cl
+    for cl in (0, 2, 4, 8, None):
+        e.set_tuning("cluster", -1 if cl is None else cl)
         r = e.run(pairs, None)
         t0 = time.perf_counter()
         for _ in range(50): r = e.run(pairs, None)
         dt = (time.perf_counter() - t0) / 50 * 1e3
         print(f"beams {beams} cluster {cl}: run {dt:.3f} ms, passes {r.iters[0]}")
-    os.environ.pop("ICPB_CLUSTER", None)
     tfs, err = gicp.icp(p1, p2)
     t0 = time.perf_counter()
     for _ in range(50): tfs, err = gicp.icp(p1, p2)

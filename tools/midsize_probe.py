@@ -16,14 +16,10 @@ out = {}
 for B in (40, 80, 120, 160, 220, 300, 450, 700, 1000, 1500):
     pairs = allp[rng.choice(len(allp), B, replace=False)].astype(np.int32)
     row = {}
-    for name, env in (("default", {}), ("c1_t256", {"ICPB_CLUSTER": "0", "ICPB_THREADS": "256"}),
-                      ("c1_t128", {"ICPB_CLUSTER": "0", "ICPB_THREADS": "128"}),
-                      ("c2_t256", {"ICPB_CLUSTER": "2", "ICPB_THREADS": "256"}),
-                      ("c4_t256", {"ICPB_CLUSTER": "4", "ICPB_THREADS": "256"}),
-                      ("c2_t128", {"ICPB_CLUSTER": "2", "ICPB_THREADS": "128"})):
-        for k in ("ICPB_CLUSTER", "ICPB_THREADS"):
-            os.environ.pop(k, None)
-        os.environ.update(env)
+    for name, (cl, thr) in (("default", (-1, 0)), ("c1_t256", (0, 256)), ("c1_t128", (0, 128)),
+                            ("c2_t256", (2, 256)), ("c4_t256", (4, 256)), ("c2_t128", (2, 128))):
+        e.set_tuning("cluster", cl)
+        e.set_tuning("threads", thr)
         r = e.run(pairs, None, epsilon=0.05)
         t0 = time.perf_counter()
         for _ in range(8):
