@@ -116,7 +116,8 @@ struct PinnedBuf {
 constexpr int kMaxSegments = 64;        // pieces of the streaming scan-table upload (icpb_align_host)
 
 struct LaunchCfg {
-    int threads, smem, n2pad_cap, n1_cap, nchunk_cap, ntile_cap, ctas_per_sm;
+    int threads, smem, ctas_per_sm;
+    icpb::SmemLayout L;
     int cluster;   // CTAs per problem (1 = ordinary launch)
 };
 
@@ -275,19 +276,8 @@ namespace {
 int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn, int R = kPointsPerThread)
 {
     if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
-    // targets padded to whole chunks, plus one all-padding chunk that idle pruning groups sweep
-    const int64_t n2pad = (longest + icpb::kChunk - 1) / icpb::kChunk * icpb::kChunk + icpb::kChunk;
-    const int64_t n1c = (longest + 3) & ~int64_t(3);
-    const int64_t nchunk = n2pad / icpb::kChunk;
     const int64_t ntile = (longest + 63) / 64;              // 64-point reduction tiles (independent of R)
     const int64_t nwork = (ntile + R / 2 - 1) / (R / 2);    // warp work items of 32*R points
-    const int64_t smem = 8 * n2pad + 16 * nchunk + 16 * (icpb::kGroups + 1) * ntile + 4 * n1c +
-                         8 * (2 * ntile * icpb::kNumSums + icpb::kMaxWarps * icpb::kTw + 2);
-    if (smem > kMaxSmem) {
-        snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
-                 (long long)longest, (long long)smem, kMaxSmem);
-        return ICPB_ETOOLONG;
-    }
     int threads = (int)(nwork * 32);                      // one warp per work item, up to 8 warps
     // Small CTAs keep more independent problems in flight per SM (less idling at the per-pass
     // barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
@@ -297,8 +287,14 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
         max_threads = h->tune_threads;                    // icpb_set_tuning("threads")
     if (threads > max_threads) threads = max_threads;
     if (threads < 32) threads = 32;
-    c->threads = threads; c->smem = (int)smem; c->n2pad_cap = (int)n2pad; c->n1_cap = (int)n1c;
-    c->nchunk_cap = (int)nchunk; c->ntile_cap = (int)ntile;
+    const icpb::SmemLayout L = icpb::smem_layout(longest, threads / 32);
+    const int64_t smem = L.bytes;
+    if (smem > kMaxSmem) {
+        snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
+                 (long long)longest, (long long)smem, kMaxSmem);
+        return ICPB_ETOOLONG;
+    }
+    c->threads = threads; c->smem = (int)smem; c->L = L;
     // Latency mode: with fewer problems than SMs and more than two tiles per warp of a CTA, spread each
     // problem over a thread-block cluster (a power of two, at most 8 CTAs) so every tile gets a warp.
     // 1,024-point scans (16 tiles, two per warp) do not qualify: the per-pass cluster barrier and the
@@ -381,7 +377,9 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.hist = p->hist_cap > 0 ? d_hist : nullptr;
     a.corr = p->corr_stride > 0 ? d_corr : nullptr;
     a.queue = h->queue + (h->launches % kQueueRing);
-    a.n2pad_cap = cfg.n2pad_cap; a.n1_cap = cfg.n1_cap; a.nchunk_cap = cfg.nchunk_cap; a.ntile_cap = cfg.ntile_cap;
+    a.n2pad_cap = cfg.L.n2pad; a.n1_cap = cfg.L.n1c; a.nchunk_cap = cfg.L.nchunk; a.ntile_cap = cfg.L.ntile;
+    a.o_tqy = cfg.L.o_tqy; a.o_cb = cfg.L.o_cb; a.o_tc = cfg.L.o_tc; a.o_mm = cfg.L.o_mm; a.o_corr = cfg.L.o_corr;
+    a.o_red = cfg.L.o_red; a.o_tw = cfg.L.o_tw; a.o_s0 = cfg.L.o_s0; a.o_scr = cfg.L.o_scr;
     a.executed = h->executed;
     a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived; a.order = d_order; a.upload_timeout = d_upload_timeout;
     a.peers = nullptr; a.n_peers = 0; a.rec_row0 = 0; a.rec_block = B > 0 ? B : 1; a.rec_stride = 0;

@@ -45,6 +45,45 @@ constexpr int   kGroups   = ICPB_G;
 constexpr int   kLpg      = 32 / kGroups;   // lanes per group
 static_assert(kGroups == 1 || kGroups == 2 || kGroups == 4 || kGroups == 8, "kGroups must be 1, 2, 4 or 8");
 
+// Dynamic shared memory of icp_align_kernel, in this order:
+//   tqx, tqy   target SoA as fp32, n2pad floats each (whole chunks + one all-padding chunk)
+//   cb         bounding circle per 16-target chunk, count rounded up to 32 (padding entries never pass)
+//   tc         bounding circle per pruning group of every source tile (untransformed source)
+//   mm         [2][tiles] (min, max) matched target index per tile
+//   corr       current correspondences
+//   red        [2][tiles][8] per-tile partial sums, double buffered by pass parity
+//   tw         [warps][8] warp-private copy of T and its stretch
+//   s0         sum of (source point - first source point)
+//   scr        [warps][7 * 33] transpose scratch of the per-tile reduction
+struct SmemLayout {
+    int32_t n2pad, nchunk, ntile, n1c;
+    int32_t o_tqy, o_cb, o_tc, o_mm, o_corr, o_red, o_tw, o_s0, o_scr, bytes;
+};
+constexpr int kScrStride = 33;                       // doubles per column of the transpose scratch
+constexpr int kScrWarp   = 7 * kScrStride + 1;       // doubles per warp (kept even)
+__host__ __device__ inline SmemLayout smem_layout(int64_t longest, int warps)
+{
+    SmemLayout L;
+    const int64_t n2pad = (longest + 15) / 16 * 16 + 16;
+    const int64_t nchunk = (n2pad / 16 + 31) / 32 * 32;
+    const int64_t ntile = (longest + 63) / 64;
+    const int64_t n1c = (longest + 3) & ~int64_t(3);
+    int64_t o = 0;
+    o += 4 * n2pad;                 L.o_tqy = (int32_t)o;
+    o += 4 * n2pad;                 L.o_cb = (int32_t)o;
+    o += 16 * nchunk;               L.o_tc = (int32_t)o;
+    o += 16 * 8 * ntile;            L.o_mm = (int32_t)o;          // room for up to 8 groups per tile
+    o += 8 * 2 * ntile;             L.o_corr = (int32_t)o;
+    o += 4 * n1c;                   L.o_red = (int32_t)o;
+    o += 8 * 2 * ntile * 8;         L.o_tw = (int32_t)o;
+    o += 8 * 32 * 8;                L.o_s0 = (int32_t)o;
+    o += 16;                        L.o_scr = (int32_t)o;
+    o += 8 * (int64_t)warps * kScrWarp;
+    L.n2pad = (int32_t)n2pad; L.nchunk = (int32_t)nchunk; L.ntile = (int32_t)ntile; L.n1c = (int32_t)n1c;
+    L.bytes = o > 0x7fffffff ? 0x7fffffff : (int32_t)o;
+    return L;
+}
+
 struct KernelArgs {
     const double  *xy;        // scan table, (sum m_i, 2) fp64
     const int64_t *offsets;   // CSR offsets, n_scans + 1
@@ -63,6 +102,9 @@ struct KernelArgs {
     int32_t        n1_cap;    // int32 slots for correspondences in shared memory
     int32_t        nchunk_cap;// chunk bounding circles in shared memory
     int32_t        ntile_cap; // source tiles (32*R points) whose partial sums live in shared memory
+    // byte offsets of the arrays in dynamic shared memory (SmemLayout, computed once by the host):
+    // a pointer is then one add away from the shared window, cheap to rematerialise
+    int32_t        o_tqy, o_cb, o_tc, o_mm, o_corr, o_red, o_tw, o_s0, o_scr;
     unsigned long long *executed; // optional: += distance evaluations actually executed
     // streaming upload (icpb_align_host): pair b may start once *arrived > seg_of_pair[b], i.e. the
     // copy engine has delivered the scan-table segment holding the later of its two scans
@@ -176,6 +218,8 @@ __device__ __forceinline__ float decision_thr(float m1, float e)
 // Rare path of the decision step: all targets j in [lo, hi) whose filter distance is <= thr are
 // evaluated exactly; keeps the lexicographic (distance, index) minimum (j ascends, so strict <
 // keeps the first index = np.argmin's rule).
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
 __device__ __forceinline__ void exact_range(int lo, int hi, float thr, float px, float py, double Px, double Py,
                                             const float *tqx, const float *tqy, const double2 *dst,
                                             double &best, int &idx)
@@ -208,10 +252,14 @@ __device__ __noinline__ int exact_decide_chunk(int j0, unsigned cand, double Px,
 }
 // (b) another chunk is within the bound: every chunk whose circle reaches within sqrt(thr) of the
 // point may hold a candidate (chunks ascend, so the first-index rule still holds across chunks)
+// (the shared arrays are addressed by their byte offsets: a generic pointer argument would make the
+// caller form -- and keep rematerialising -- 64-bit generic addresses of shared memory)
 __device__ __noinline__ int exact_decide_all(int nchunks, int n2, int fallback, float thr, float px, float py,
-                                             double Px, double Py, const float *tqx, const float *tqy,
-                                             const float4 *cb, const double2 *dst)
+                                             double Px, double Py, int o_tqy, int o_cb, const double2 *dst)
 {
+    const float *tqx = reinterpret_cast<const float *>(smem_raw);
+    const float *tqy = reinterpret_cast<const float *>(smem_raw + o_tqy);
+    const float4 *cb = reinterpret_cast<const float4 *>(smem_raw + o_cb);
     double best = __longlong_as_double(0x7ff0000000000000LL);
     int idx = fallback;
     const float s = sqrt_fast(thr) * 1.0001f + 1e-30f;
@@ -368,16 +416,15 @@ template <int R, bool PRUNE, bool CLUSTER>
 __global__ void __launch_bounds__(256, (CLUSTER ? 1 : (R >= 4 ? 2 : ICPB_MIN_CTAS)))
 icp_align_kernel(const KernelArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     float  *tqx    = reinterpret_cast<float *>(smem_raw);
-    float  *tqy    = tqx + a.n2pad_cap;
-    float4 *cb     = reinterpret_cast<float4 *>(tqy + a.n2pad_cap);          // chunk circle (cx, cy, r, -)
-    float4 *tc     = cb + a.nchunk_cap;                                      // tile circle, untransformed source
-    int2   *mm     = reinterpret_cast<int2 *>(tc + a.ntile_cap * kGroups);             // [2][ntile_cap] (min, max) matched index per tile
-    int    *corr_s = reinterpret_cast<int *>(mm + 2 * a.ntile_cap);
-    double *red    = reinterpret_cast<double *>(corr_s + ((a.n1_cap + 3) & ~3));   // [2][ntile_cap][8]
-    double *Tw     = red + 2 * a.ntile_cap * kNumSums;                       // [kMaxWarps][8] per-warp copy of T
-    double *S0     = Tw + kMaxWarps * kTw;                                   // sum of (source - first source point)
+    float  *tqy    = reinterpret_cast<float *>(smem_raw + a.o_tqy);
+    float4 *cb     = reinterpret_cast<float4 *>(smem_raw + a.o_cb);          // chunk circle (cx, cy, r', -)
+    float4 *tc     = reinterpret_cast<float4 *>(smem_raw + a.o_tc);          // group circles, untransformed source
+    int2   *mm     = reinterpret_cast<int2 *>(smem_raw + a.o_mm);            // [2][ntile_cap] (min, max) matched index per tile
+    int    *corr_s = reinterpret_cast<int *>(smem_raw + a.o_corr);
+    double *red    = reinterpret_cast<double *>(smem_raw + a.o_red);         // [2][ntile_cap][8]
+    double *Tw     = reinterpret_cast<double *>(smem_raw + a.o_tw);          // [kMaxWarps][8] per-warp copy of T
+    double *S0     = reinterpret_cast<double *>(smem_raw + a.o_s0);          // sum of (source - first source point)
     __shared__ long long s_pid;
     __shared__ unsigned int s_qmax_bits;
     __shared__ int s_tile_ctr[2];
@@ -386,6 +433,7 @@ icp_align_kernel(const KernelArgs a)
     const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const float kInf = __int_as_float(0x7f800000);
     double *Tmine = Tw + warp * kTw;
+    double *scr = reinterpret_cast<double *>(smem_raw + a.o_scr) + warp * kScrWarp;   // reduction scratch of this warp
     unsigned int executed = 0;
     namespace cg = cooperative_groups;
     int crank = 0, csize = 1;
@@ -537,8 +585,12 @@ icp_align_kernel(const KernelArgs a)
             const float cx = 0.5f * (lx + hx), cy = 0.5f * (ly + hy);
             float r2 = 0.0f;
             for (int j = j0; j < j1; ++j) r2 = fmaxf(r2, dist32(cx, cy, tqx[j], tqy[j]));
-            cb[c] = make_float4(cx, cy, sqrtf(r2) * 1.00001f, 0.0f);
+            // radius with the safety factors of the chunk test folded in: (reach + r) 1.00001 there
+            cb[c] = make_float4(cx, cy, sqrtf(r2) * 1.00001f * 1.00001f, 0.0f);
         }
+        // padding entries up to a multiple of 32 chunks: so far away that no test passes
+        for (int c = nchunks + tid; c < ((nchunks + 31) & ~31); c += NT)
+            cb[c] = make_float4(kPadCoord, kPadCoord, 0.0f, 0.0f);
         if (tid == NT - 1) {                                      // fixed order: tile 0, 1, 2, ...
             double ax = 0.0, ay = 0.0;
             for (int t = 0; t < ntiles; ++t) {
@@ -668,24 +720,35 @@ icp_align_kernel(const KernelArgs a)
                     // every target within sqrt(ubmax) of some point of the group lies within `reach`
                     // of the group centre; e covers the fp32 rounding of the centres and differences
                     const float e = 4.0f * 1.1920929e-7f * (pmax + qmax);
-                    const float reach = (rho + sqrt_fast(ubmax)) * 1.0001f + 2.0f * e;
+                    const float reach = ((rho + sqrt_fast(ubmax)) * 1.0001f + 2.0f * e) * 1.00001f;
+                    const u64 TC = pack2(tcx, tcy);
 
                     for (int cbase = 0; cbase < nchunks; cbase += 32) {
                         // chunks of this block that the group has to sweep: lane li of the group tests
                         // chunks cbase + li, cbase + kLpg + li, ... against the group's circle
-                        unsigned mask = 0;
+                        // (padding circles beyond nchunks never pass: no bounds check)
+                        unsigned mask = 0, bal[kGroups];
 #pragma unroll
                         for (int j = 0; j < kGroups; ++j) {
-                            const int c = cbase + j * kLpg + li;
-                            bool nd = c < nchunks;
-                            if (nd) {
-                                const float4 b = cb[c];
-                                const float lim = (reach + b.z) * 1.00001f;
-                                nd = dist32(tcx, tcy, b.x, b.y) <= lim * lim;
-                            }
-                            const unsigned bal = __ballot_sync(0xffffffffu, nd);
-                            if (kGroups == 1) mask = bal;
-                            else mask |= ((bal >> (grp * kLpg)) & ((1u << (kLpg & 31)) - 1u)) << ((j * kLpg) & 31);
+                            const float4 b = cb[cbase + j * kLpg + li];
+                            float dx2, dy2;
+                            const u64 dd = sub2(pack2(b.x, b.y), TC);
+                            unpack2(mul2(dd, dd), dx2, dy2);
+                            const float lim = reach + b.z;
+                            bal[j] = __ballot_sync(0xffffffffu, dx2 + dy2 <= lim * lim);
+                        }
+                        if (kGroups == 1) {
+                            mask = bal[0];
+                        } else if (kGroups == 4) {              // byte grp of every ballot, by byte permutes
+                            const unsigned sel = (unsigned)grp | ((unsigned)(4 + grp) << 4);
+                            mask = __byte_perm(__byte_perm(bal[0], bal[1], sel), __byte_perm(bal[2], bal[3], sel), 0x5410);
+                        } else if (kGroups == 2) {              // 16-bit half grp of both ballots
+                            const unsigned h = 2u * (unsigned)grp;
+                            mask = __byte_perm(bal[0], bal[1], h | ((h + 1) << 4) | ((h + 4) << 8) | ((h + 5) << 12));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < kGroups; ++j)
+                                mask |= ((bal[j] >> (grp * kLpg)) & ((1u << (kLpg & 31)) - 1u)) << ((j * kLpg) & 31);
                         }
                         // the warp takes as many steps as its busiest group; a group that has run out of
                         // chunks sweeps the all-padding chunk (index nchunks), which changes nothing
@@ -750,7 +813,7 @@ icp_align_kernel(const KernelArgs a)
                             const unsigned acc = (acc0 << 8) | acc1;
                             int idx = j0 + __clz((int)acc) - 16;  // unique candidate: no fp64 needed
                             if (m2[r] <= thr)                    // another chunk is within the bound
-                                idx = exact_decide_all(nchunks, n2, j0, thr, px[r], py[r], Px, Py, tqx, tqy, cb, dst);
+                                idx = exact_decide_all(nchunks, n2, j0, thr, px[r], py[r], Px, Py, a.o_tqy, a.o_cb, dst);
                             else if (acc & (acc - 1))            // more than one candidate in the chunk
                                 idx = exact_decide_chunk(j0, __brev(acc) >> 16, Px, Py, dst);
                             else if (acc == 0)                   // (non-finite input: keep a valid index)
@@ -768,9 +831,26 @@ icp_align_kernel(const KernelArgs a)
                     }
                     const int rt = tile * SUBT + sub;                           // reduction tile
                     if (rt < ntiles) {                                       // warp-uniform
-                        const double tot = warp_sum8(sum, lane);             // lane L: total of column id(L), see warp_sum8
-                        if ((lane & 3) == 0)
-                            redp[rt * kNumSums + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
+                        // Warp total of the 7 sums through the transpose scratch: every lane stores its
+                        // values (column k at k*33 + lane: conflict free), lane k + 8*part adds column k
+                        // over lanes 8*part .. 8*part + 7 in lane order, two butterfly levels add the four
+                        // parts.  Fixed order -> deterministic; ~37 instructions against ~77 for a shuffle
+                        // butterfly with its register selects.
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) scr[k * kScrStride + lane] = sum[k];
+                        __syncwarp();
+                        double tot = 0.0;
+                        {
+                            const double *col = scr + (lane & 7) * kScrStride + (lane >> 3) * 8;
+                            if ((lane & 7) < 7) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) tot += col[j];
+                            }
+                        }
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+                        if (lane < 7) redp[rt * kNumSums + lane] = tot;
+                        __syncwarp();
                         imin = __reduce_min_sync(0xffffffffu, imin); imax = __reduce_max_sync(0xffffffffu, imax);
                         if (lane == 0) mmp[rt] = make_int2(imin, imax);
                     }
