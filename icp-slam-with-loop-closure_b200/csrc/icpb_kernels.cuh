@@ -41,6 +41,10 @@ constexpr int   kTw       = 8;        // doubles per warp-private transform reco
 #ifndef ICPB_G
 #define ICPB_G 4
 #endif
+#ifndef ICPB_EXH_UNROLL
+#define ICPB_EXH_UNROLL 1
+#endif
+constexpr int   kExhUnroll = ICPB_EXH_UNROLL;     // chunk-loop unrolling of the exhaustive variant
 constexpr int   kGroups   = ICPB_G;
 constexpr int   kLpg      = 32 / kGroups;   // lanes per group
 static_assert(kGroups == 1 || kGroups == 2 || kGroups == 4 || kGroups == 8, "kGroups must be 1, 2, 4 or 8");
@@ -177,13 +181,38 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0,
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// Packed or scalar?  Measured on B200 (profiles/r02_micro_pipes.log): scalar FADD/FMUL/FFMA issue at
+// 3.9 warp-instructions per clock per SM, packed f32x2 at 1.98 (the same 126 lanes per clock), and a
+// packed instruction does NOT overlap with an ALU-pipe instruction (FMNMX3, SEL, SHF, LOP3: 1.98 per
+// clock on their own) -- FFMA2 and FMNMX3 alternating run at 0.99 + 0.99 -- while a scalar FFMA does
+// (1.78 + 1.78).  So the all-packed sweep pays for its min tree in full: 4 x 2 + 1 x 2 = 10 cycles per
+// 64 distances, an attainable 25.6 distances per clock per SM against the 32 of the FP32 pipe alone;
+// the isolated loop reaches 98% of that (profiles/r02_micro_sweep.log).  Computing ICPB_MIX of every
+// four targets with scalar instructions (same IEEE operation per element, bit-identical distances)
+// should let the ALU work issue underneath them; in the kernel it did not pay (chain 1.51 ms either
+// way, exhaustive variant 69% -> 66% with 2 of 4 scalar, 60% all scalar: more issue slots, and the
+// kernel runs at 16-24 warps per SM where the mix is latency-bound), so the default stays packed.
+#ifndef ICPB_MIX
+#define ICPB_MIX 0
+#endif
+constexpr int kMixScalar = ICPB_MIX;      // 0, 2 or 4 of every 4 targets use scalar FADD/FMUL/FFMA
+
 // filter distances of one source point to four targets (x0..x3, y0..y3)
-__device__ __forceinline__ void dist32x4(u64 PX, u64 PY, const float4 &X, const float4 &Y, float *d)
+__device__ __forceinline__ void dist32x4(float px, float py, const float4 &X, const float4 &Y, float *d)
 {
-    const u64 dxa = sub2(pack2(X.x, X.y), PX), dya = sub2(pack2(Y.x, Y.y), PY);
-    const u64 dxb = sub2(pack2(X.z, X.w), PX), dyb = sub2(pack2(Y.z, Y.w), PY);
-    unpack2(fma2(dya, dya, mul2(dxa, dxa)), d[0], d[1]);
-    unpack2(fma2(dyb, dyb, mul2(dxb, dxb)), d[2], d[3]);
+    const u64 PX = pack2(px, px), PY = pack2(py, py);
+    if (kMixScalar < 4) {
+        const u64 dxa = sub2(pack2(X.x, X.y), PX), dya = sub2(pack2(Y.x, Y.y), PY);
+        unpack2(fma2(dya, dya, mul2(dxa, dxa)), d[0], d[1]);
+    } else {
+        d[0] = dist32(px, py, X.x, Y.x); d[1] = dist32(px, py, X.y, Y.y);
+    }
+    if (kMixScalar < 2) {
+        const u64 dxb = sub2(pack2(X.z, X.w), PX), dyb = sub2(pack2(Y.z, Y.w), PY);
+        unpack2(fma2(dyb, dyb, mul2(dxb, dxb)), d[2], d[3]);
+    } else {
+        d[2] = dist32(px, py, X.z, Y.z); d[3] = dist32(px, py, X.w, Y.w);
+    }
 }
 
 __device__ __forceinline__ float min3f(float a, float b, float c)
@@ -368,12 +397,26 @@ __device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
 // is <= thr / (1 + 8u) (u = 2^-24): with s = dx*dx + dy*dy <= thr (1 + 3u) / (1 + 8u) the exact value
 // s - thr is below -4u thr, and the one rounding before the sign is taken moves it by at most
 // u max(dx*dx, thr).  Same four packed instructions as a distance.
-__device__ __forceinline__ void dist32x4_minus(u64 PX, u64 PY, u64 NTHR, const float4 &X, const float4 &Y, float *e)
+__device__ __forceinline__ float dist32_minus(float px, float py, float nthr, float qx, float qy)
 {
-    const u64 dxa = sub2(pack2(X.x, X.y), PX), dya = sub2(pack2(Y.x, Y.y), PY);
-    const u64 dxb = sub2(pack2(X.z, X.w), PX), dyb = sub2(pack2(Y.z, Y.w), PY);
-    unpack2(fma2(dya, dya, fma2(dxa, dxa, NTHR)), e[0], e[1]);
-    unpack2(fma2(dyb, dyb, fma2(dxb, dxb, NTHR)), e[2], e[3]);
+    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py);
+    return __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, nthr));
+}
+__device__ __forceinline__ void dist32x4_minus(float px, float py, float nthr, const float4 &X, const float4 &Y, float *e)
+{
+    const u64 PX = pack2(px, px), PY = pack2(py, py), NTHR = pack2(nthr, nthr);
+    if (kMixScalar < 4) {
+        const u64 dxa = sub2(pack2(X.x, X.y), PX), dya = sub2(pack2(Y.x, Y.y), PY);
+        unpack2(fma2(dya, dya, fma2(dxa, dxa, NTHR)), e[0], e[1]);
+    } else {
+        e[0] = dist32_minus(px, py, nthr, X.x, Y.x); e[1] = dist32_minus(px, py, nthr, X.y, Y.y);
+    }
+    if (kMixScalar < 2) {
+        const u64 dxb = sub2(pack2(X.z, X.w), PX), dyb = sub2(pack2(Y.z, Y.w), PY);
+        unpack2(fma2(dyb, dyb, fma2(dxb, dxb, NTHR)), e[2], e[3]);
+    } else {
+        e[2] = dist32_minus(px, py, nthr, X.z, Y.z); e[3] = dist32_minus(px, py, nthr, X.w, Y.w);
+    }
 }
 
 // Largest singular value of the linear part of T (a bound on how much T stretches a distance), as
@@ -642,9 +685,8 @@ icp_align_kernel(const KernelArgs a)
                 // smallest filter distance of point r to the 16 targets of a staged chunk
                 auto chunk_min = [&](const float4 (&X)[4], const float4 (&Y)[4], int r) -> float {
                     float d[16];
-                    const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) dist32x4(PX, PY, X[v], Y[v], d + 4 * v);
+                    for (int v = 0; v < 4; ++v) dist32x4(px[r], py[r], X[v], Y[v], d + 4 * v);
                     float cm = min3f(d[0], d[1], d[2]);
                     cm = min3f(cm, d[3], d[4]);
                     cm = min3f(cm, d[5], d[6]);
@@ -769,7 +811,7 @@ icp_align_kernel(const KernelArgs a)
                     pm = warp_max_nonneg(pm);
                     tol_e = 2.0f * 5.9604645e-8f * (pm + qmax) * 1.0001f;
                     executed += (unsigned)nchunks;
-#pragma unroll 1
+#pragma unroll kExhUnroll
                     for (int c = 0; c < nchunks; ++c) sweep(c);
                 }
                 // ---- exact decision among the filter's candidates, then the fit sums ----
@@ -798,11 +840,9 @@ icp_align_kernel(const KernelArgs a)
                             {
                                 const float4 *bx = reinterpret_cast<const float4 *>(tqx + j0);
                                 const float4 *by = reinterpret_cast<const float4 *>(tqy + j0);
-                                const u64 PX = pack2(px[r], px[r]), PY = pack2(py[r], py[r]);
-                                const u64 NTHR = pack2(-thr, -thr);
                                 float e[16];
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) dist32x4_minus(PX, PY, NTHR, bx[v], by[v], e + 4 * v);
+                                for (int v = 0; v < 4; ++v) dist32x4_minus(px[r], py[r], -thr, bx[v], by[v], e + 4 * v);
 #pragma unroll
                                 for (int k = 0; k < 8; ++k) {
                                     acc0 = __funnelshift_l(__float_as_uint(e[k]), acc0, 1);
