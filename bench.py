@@ -1,31 +1,41 @@
 #!/usr/bin/env python
 """Benchmark of the batched ICP hot path: ICP scan-pair alignments / second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): the full odometry ICP chain over a 5,000-scan synthetic
-indoor trajectory, 1,024-beam scans, pairs (i, i-1) with the odometry initial guess, epsilon 0.05,
-max_iters 100 (reference scripts/main.py:240-247).  One step = one pass of the hot path over the
-whole 4,999-pair batch.  With N GPUs every rank aligns its own 4,999-pair chain (weak scaling)
-and an NCCL all-gather returns every pair's constraint record to all ranks.
+Workloads (BASELINE.json configs; `--workload`):
+  chain      configs[1], the headline: the full odometry ICP chain over a 5,000-scan synthetic indoor
+             trajectory, 1,024-beam scans, pairs (i, i-1) with the odometry initial guess, epsilon 0.05,
+             max_iters 100 (reference scripts/main.py:240-247).  One step = one pass of the hot path
+             over the whole 4,999-pair batch.  With N GPUs every rank aligns its OWN chain: weak scaling.
+  proximity  configs[2]: every pair of the trajectory within 1 m and at least 2 m along the path
+             (~100,000 pairs, identity initial guess).  ONE pair list, sharded over the ranks in
+             interleaved blocks against a replicated scan table: strong scaling.
+  allpairs   configs[3] in miniature (--scans 600 by default): every pair i<j, decoded on the device
+             from a linear index, interleaved blocks per rank: strong scaling.
+  highres    configs[4]: 4,096-beam scans, 32 initial headings per pair.
+On every multi-GPU run the exchange of the constraint records is fused into the alignment kernel: its
+epilogue stores each finished pair's 64-byte record into every rank's gather buffer over NVLink peer
+memory (icp_slam_b200.dist.FusedGather); one symmetric-memory barrier follows, no collective.
 
 `value`     device-timed: scan table, pairs and initial guesses already resident in HBM.
-`e2e`       the same step through the public host API (IcpEngine.align = the C ABI's
-            icpb_align_host: segmented upload overlapped with the kernels): pinned host buffers in,
-            results out in host memory.
-`roofline`  FP32-pipe roofline of the alignment kernel: algorithmic
-            point-pair distance evaluations (sum over pairs of passes*N1*N2) per second against
-            SMs * 128 lanes * f_max / 4 instruction slots.
-`cpu_baseline` the C port of the reference algorithm (oracle/icp_oracle.c) on all host cores.
+`e2e`       the same step through the public host API, IcpEngine.align, fed what the reference feeds
+            its fan-out: `lidar_points`, a Python list of separate pageable (m_i, 2) float64 arrays
+            (reference src/dataloader.py:110-112), plus the pair list and (B, 3, 3) initial guesses in
+            host memory; results (and, on N GPUs, every rank's gathered records) back in host memory.
+`roofline`  FP32-pipe view of the timed kernel: `frac` is the share of the pipe's lane-slots the
+            kernel actually used (executed distance evaluations x 4 slots); the algorithmic speed-up
+            of the pruning and the exhaustive variant (the one the pipe roofline bounds) sit beside it.
+`cpu_baseline` the C port of the reference algorithm (oracle/icp_oracle.c) on all host cores, and the
+            unmodified numpy reference under joblib when it can be imported on this machine.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -35,41 +45,61 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 4,999-pair chain, from the
-# committed `ncu --set full` capture (profiles/r01m_align_ncu_full_summary.csv); None until measured
-TRAFFIC_NCU = 85.1e6   # 81.1 MB read (= one pass over the 81 MB scan table) + 4.0 MB written
-WARP_INSTR_NCU = 1405949366.0   # smsp__inst_executed.sum of the same launch (same capture)
 METRIC = "icp_scan_pair_alignments_per_sec"
 UNIT = "pairs/s"
 SEED = 467002
+EPS, MAX_ITERS = 0.05, 100
+# counters of the timed kernel from a committed `ncu --set full` capture of this same command
+# (written by tools/ncu_summary.py; carries the commit it was taken at)
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_align_ncu_summary.json")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scans", type=int, default=5000, help="scans in the chain (config: 5000)")
-    ap.add_argument("--beams", type=int, default=1024, help="beams per scan (config: 1024)")
     ap.add_argument("--workload", default="chain", choices=["chain", "proximity", "allpairs", "highres"])
+    ap.add_argument("--scans", type=int, default=0, help="scans of the trajectory (default: per workload)")
+    ap.add_argument("--beams", type=int, default=0, help="beams per scan (default: per workload)")
     ap.add_argument("--pairs", type=int, default=0, help="cap on the pair count of the non-chain workloads")
+    ap.add_argument("--block", type=int, default=256, help="interleaved block of the strong-scaling partition")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU sample")
     ap.add_argument("--exhaustive", action="store_true", help="run the timed steps with pruning off (profiling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
-    return ap.parse_args()
+    ap.add_argument("--no-sustained", action="store_true", help="skip the sustained-clock segment")
+    args = ap.parse_args()
+    dflt = {"chain": (5000, 1024), "proximity": (5000, 1024), "allpairs": (600, 1024), "highres": (48, 4096)}
+    args.scans = args.scans or dflt[args.workload][0]
+    args.beams = args.beams or dflt[args.workload][1]
+    args.strong = args.workload in ("proximity", "allpairs")
+    return args
+
+
+def config_of(args, world):
+    """The workload description both arms print (same function, same strings)."""
+    name = {"chain": f"odometry ICP chain, {args.scans} scans x {args.beams} beams, pairs (i, i-1), odometry "
+                     f"initial guess (BASELINE configs[1]); every GPU its own chain",
+            "proximity": f"proximity loop-closure candidates of a {args.scans}-scan x {args.beams}-beam trajectory, "
+                         f"identity initial guess (BASELINE configs[2]); one pair list sharded over the GPUs",
+            "allpairs": f"all pairs i<j of {args.scans} scans x {args.beams} beams, identity initial guess "
+                        f"(BASELINE configs[3]); one index space sharded over the GPUs",
+            "highres": f"32-start heading sweep, {args.scans} scans x {args.beams} beams (BASELINE configs[4])"}
+    return {"workload": name[args.workload], "scans": args.scans, "beams": args.beams,
+            "epsilon": EPS, "max_iters": MAX_ITERS, "n_gpus": world,
+            "l2": "GPU arm: L2 flushed between timed steps (768 MB fill, outside the timed events)"}
 
 
 def workload(args, rank, world):
-    """Synthetic scans + pair list + initial guesses of one rank.  `chain` is the headline
-    workload (BASELINE configs[1]); the others are the remaining BASELINE configs at a size that
-    fits a default run, for information (python bench.py --workload ...)."""
+    """Synthetic scans + pair list + initial guesses.  `chain`/`highres`: every rank its own stretch of
+    the trajectory (weak scaling); `proximity`/`allpairs`: the same table and pair list on every rank."""
     from icp_slam_b200 import synth
-    # each rank owns a different stretch of the trajectory and its own noise/odometry seed
-    rng_seed = SEED + 1000 * rank
+    own = 0 if args.strong else rank
+    rng_seed = SEED + 1000 * own
     rng = np.random.default_rng(rng_seed)
-    phase = rank / max(world, 1)
+    phase = own / max(world, 1)
     if args.workload == "chain":            # configs[1]: scripts/main.py:239-247
         poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=phase)
         scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
@@ -77,22 +107,17 @@ def workload(args, rank, world):
         idx = np.arange(1, args.scans)
         pairs = np.stack((idx, idx - 1), axis=1).astype(np.int32)
         init = np.stack([synth.pose_to_mat(odo[i] - odo[i - 1]) for i in idx])
-        args.label = f"odometry chain {args.scans} scans x {args.beams} beams per GPU (configs[1])"
     elif args.workload == "proximity":      # configs[2]: all pairs within 1 m, >= 2 m along the path
         poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=phase)
         scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
         pairs = synth.proximity_pairs(poses, max_pairs=args.pairs or 100000, seed=rng_seed)
-        init = np.broadcast_to(np.eye(3), (len(pairs), 3, 3)).copy()
-        args.label = f"proximity loop-closure candidates, {args.scans} scans x {args.beams} beams (configs[2])"
+        init = None
     elif args.workload == "allpairs":       # configs[3]: exhaustive i<j, source j onto target i
         poses = synth.loop_trajectory(args.scans, step=180.0 / args.scans, start_phase=phase)
         scans = synth.scans_from_poses(poses, args.beams, rng, drop_frac=0.03)
         ij = synth.all_pairs_decode(np.arange(synth.all_pairs_count(args.scans)), args.scans)
         pairs = np.stack((ij[:, 1], ij[:, 0]), axis=1).astype(np.int32)
-        if args.pairs and args.pairs < len(pairs):
-            pairs = pairs[np.sort(rng.choice(len(pairs), args.pairs, replace=False))]
-        init = np.broadcast_to(np.eye(3), (len(pairs), 3, 3)).copy()
-        args.label = f"all pairs i<j of {args.scans} scans x {args.beams} beams (configs[3])"
+        init = None
     else:                                   # configs[4]: high-resolution scans, multi-start heading sweep
         k_starts = 32
         poses = synth.loop_trajectory(args.scans, step=0.04, start_phase=phase)
@@ -101,54 +126,58 @@ def workload(args, rank, world):
         pairs = np.stack((idx, idx - 1), axis=1).astype(np.int32)
         th = np.tile(-np.pi + 2 * np.pi * np.arange(k_starts) / k_starts, args.scans - 1)
         init = np.stack([synth.pose_to_mat((0.0, 0.0, t)) for t in th])
-        args.label = f"{k_starts}-start heading sweep, {args.scans} scans x {args.beams} beams (configs[4])"
     return scans, pairs, init
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (profiling guide)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons polled through NVML every ~2 ms during the timed region (the timed
+    region of the headline workload is tens of milliseconds: nvidia-smi's 100 ms loop sees two samples)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:                                    # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:                                # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+    def window(self, t0, t1):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        sm, reasons = [], set()
+        for ts, mhz, bits in list(self.rows):
+            if t0 <= ts <= t1:
+                sm.append(mhz)
+                reasons |= {n for n, b in names if bits & b}
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": ["no samples in the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        self.stop_flag = True
 
 
 _ALL_CPUS = None
@@ -157,8 +186,7 @@ _ALL_CPUS = None
 def bind_to_gpu_numa_node(index):
     """One process per GPU: run this rank's host threads on the CPUs next to its GPU, so the pinned
     staging buffers (first touch) and the copy-engine reads stay on the local memory controller and
-    PCIe root -- with 8 ranks uploading at once the cross-socket link is otherwise shared by all of
-    them.  Returns a short description for the JSON line; never fatal."""
+    PCIe root.  Returns a short description for the JSON line; never fatal."""
     global _ALL_CPUS
     try:
         _ALL_CPUS = os.sched_getaffinity(0)
@@ -172,62 +200,111 @@ def bind_to_gpu_numa_node(index):
         return f"unbound ({type(exc).__name__})"
 
 
-def cpu_port_rate(scans, pairs, init, seconds, threads=0):
+def identity_init(n):
+    return np.broadcast_to(np.eye(3), (n, 3, 3)).copy()
+
+
+def cpu_port_rate(scans, pairs, init, seconds, threads=0, all_pairs=False):
     """Time the C port of the reference algorithm on a bounded sample of the same workload."""
     from oracle import c_oracle
     c_oracle.build()
     nthr = threads or c_oracle.max_threads()
     xy, off = c_oracle.pack(scans)
+    init = identity_init(len(pairs)) if init is None else init
     rng = np.random.default_rng(SEED)
-    order = rng.permutation(len(pairs))
+    order = np.arange(len(pairs)) if all_pairs else rng.permutation(len(pairs))
     probe = order[:max(2 * nthr, 8)]
     t = time.perf_counter()
-    c_oracle.icp_batch(xy, off, pairs[probe], init[probe], epsilon=0.05, max_iters=100, n_threads=nthr)
+    c_oracle.icp_batch(xy, off, pairs[probe], init[probe], epsilon=EPS, max_iters=MAX_ITERS, n_threads=nthr)
     dt = time.perf_counter() - t
-    n = int(min(len(pairs), max(len(probe), len(probe) * seconds / max(dt, 1e-3))))
+    n = len(pairs) if all_pairs else int(min(len(pairs), max(len(probe), len(probe) * seconds / max(dt, 1e-3))))
     sel = order[:n]
     t = time.perf_counter()
-    _, _, passes = c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=0.05, max_iters=100, n_threads=nthr)
+    _, _, passes = c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=EPS, max_iters=MAX_ITERS, n_threads=nthr)
     dt = time.perf_counter() - t
     return n / dt, nthr, n, dt, float(passes.mean())
 
 
+def numpy_reference_rate(scans, pairs, init, seconds):
+    """The UNMODIFIED reference -- src.icp.icp under joblib.Parallel(n_jobs=-1, backend="loky"), exactly
+    the expression of reference scripts/main.py:240-247 -- when its source tree can be imported on this
+    machine (baseline/_ref or /root/reference; it is not shipped with this repository, so on a GPU box
+    this leg normally reports why it did not run)."""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.exists(os.path.join(root, "src", "icp.py")):
+            break
+    else:
+        return {"unavailable": "reference source tree not present on this machine (pure Python, not shipped)"}
+    try:
+        sys.path.insert(0, root)
+        from joblib import Parallel, delayed
+        from src import icp as ref_icp                       # the reference's own module, unmodified
+        ncpu = os.cpu_count() or 1
+        init = identity_init(len(pairs)) if init is None else init
+        rng = np.random.default_rng(SEED)
+        sel = rng.permutation(len(pairs))[:max(2 * ncpu, 8)]
+        hom = lambda s: np.c_[s, np.ones(len(s))]            # noqa: E731  (scripts/main.py:242-243)
+
+        def go(idx):
+            with Parallel(n_jobs=-1, backend="loky") as par:
+                t = time.perf_counter()
+                par(delayed(ref_icp.icp)(hom(scans[pairs[b, 0]]), hom(scans[pairs[b, 1]]), init[b].copy(),
+                                         max_iters=MAX_ITERS, epsilon=EPS) for b in idx)
+                return time.perf_counter() - t
+        dt = go(sel)                                          # includes the worker start-up
+        n = int(min(len(pairs), max(len(sel), len(sel) * seconds / max(dt, 1e-3))))
+        sel = rng.permutation(len(pairs))[:n]
+        dt = go(sel)
+        return {"value": n / dt, "unit": UNIT, "cores": ncpu, "kind": "reference",
+                "sample": f"{n} pairs (seeded random subsample) in {dt:.1f} s, unmodified src.icp.icp under "
+                          f"joblib.Parallel(n_jobs=-1, backend='loky') from {root}"}
+    except Exception as exc:                                  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    finally:
+        if sys.path and sys.path[0] == root:
+            sys.path.pop(0)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
-    Python and is not present on the GPU box, so this times its C port (oracle/icp_oracle.c, the
-    one place besides cpu_baseline where bench.py executes oracle/) on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores.  The
+    reference is pure Python and does not travel to the GPU box, so this times its C port
+    (oracle/icp_oracle.c, the one place besides cpu_baseline where bench.py executes oracle/) with all
+    host threads; a step is one pass over the whole pair list of the chain (4,999 pairs), a seeded
+    subsample sized for a few minutes in total for the larger workloads."""
     if rank != 0:
         return
-    scans, pairs, init = workload(args, 0, 1)
+    scans, pairs, init = workload(args, 0, world)
     from oracle import c_oracle
     c_oracle.build()
     nthr = c_oracle.max_threads()
     xy, off = c_oracle.pack(scans)
+    init = identity_init(len(pairs)) if init is None else init
     rng = np.random.default_rng(SEED)
     order = rng.permutation(len(pairs))
-    # size one step so that warmup + steps end within ~2 minutes
     probe = order[:max(2 * nthr, 8)]
     t = time.perf_counter()
-    c_oracle.icp_batch(xy, off, pairs[probe], init[probe], epsilon=0.05, max_iters=100, n_threads=nthr)
+    c_oracle.icp_batch(xy, off, pairs[probe], init[probe], epsilon=EPS, max_iters=MAX_ITERS, n_threads=nthr)
     dt = time.perf_counter() - t
-    budget = 100.0 / max(args.steps + args.warmup, 1)
+    budget = 240.0 / max(args.steps + args.warmup, 1)
     n = int(min(len(pairs), max(len(probe), len(probe) * budget / max(dt, 1e-3))))
-    sel = order[:n]
+    if args.workload == "chain" and len(pairs) * dt / len(probe) * (args.steps + args.warmup) < 900.0:
+        n = len(pairs)                                        # the whole batch per step, like the GPU arm
+    sel = np.arange(len(pairs)) if n == len(pairs) else order[:n]
     for _ in range(args.warmup):
-        c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=0.05, max_iters=100, n_threads=nthr)
+        c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=EPS, max_iters=MAX_ITERS, n_threads=nthr)
     t = time.perf_counter()
     for _ in range(args.steps):
-        c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=0.05, max_iters=100, n_threads=nthr)
+        c_oracle.icp_batch(xy, off, pairs[sel], init[sel], epsilon=EPS, max_iters=MAX_ITERS, n_threads=nthr)
     dt = time.perf_counter() - t
     rate = n * args.steps / dt
-    sample = f"{n} of {len(pairs)} chain pairs per step, seeded random subsample, {nthr} threads"
+    sample = (f"{n} of {len(pairs)} pairs per step" + ("" if n == len(pairs) else ", seeded random subsample") +
+              f", C port oracle/icp_oracle.c on {nthr} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": args.label,
-                   "pairs_per_step": n, "epsilon": 0.05, "max_iters": 100},
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_of(args, world),
+        "details": {"pairs_per_step": n},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -246,6 +323,7 @@ def main():
     import torch
     import torch.distributed as dist
     from icp_slam_b200 import icp as gicp
+    from icp_slam_b200 import dist as gdist
 
     numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
@@ -259,55 +337,53 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     scans, pairs, init = workload(args, rank, world)
-    B = len(pairs)
+    n_total = len(pairs)                                     # problems of this rank's index space
+    # ---- partition: weak = everything this rank generated; strong = interleaved blocks of one list ----
+    if args.strong and world > 1:
+        mine = gdist.shard_indices(n_total, rank, world, args.block)
+    else:
+        mine = np.arange(n_total)
+    B = len(mine)
+    pairs_mine = np.ascontiguousarray(pairs[mine])
+    init_mine = None if init is None else np.ascontiguousarray(init[mine])
     eng = gicp.IcpEngine(local)
     table = gicp.ScanTable(scans)
-    # pinned host copies (the e2e leg's sources) and HBM-resident copies (the `value` leg)
-    xy_pin = torch.from_numpy(table.xy).pin_memory()
-    off_pin = torch.from_numpy(table.offsets).pin_memory()
-    pairs_pin = torch.from_numpy(pairs).pin_memory()
-    init6 = np.ascontiguousarray(init[:, :2, :].reshape(B, 6))
-    init_pin = torch.from_numpy(init6).pin_memory()
-    xy_t, off_t = xy_pin.to(dev), off_pin.to(dev)
-    pairs_t, init_t = pairs_pin.to(dev), init_pin.to(dev)
+    lens = table.lengths
+    xy_t, off_t = torch.from_numpy(table.xy).to(dev), torch.from_numpy(table.offsets).to(dev)
+    pairs_t = torch.from_numpy(pairs_mine).to(dev)
+    init_t = None if init_mine is None else torch.from_numpy(np.ascontiguousarray(init_mine[:, :2, :].reshape(B, 6))).to(dev)
     eng.set_scans_device(xy_t, off_t, table)
-    # constraint records: [T(6), err, passes] as 8 float64 per pair
-    rec = torch.empty((B, 8), dtype=torch.float64, device=dev)
     out_T = torch.empty((B, 6), dtype=torch.float64, device=dev)
     out_err = torch.empty(B, dtype=torch.float64, device=dev)
     out_pass = torch.empty(B, dtype=torch.int32, device=dev)
-    gathered, symm = None, None
+    # the all-pairs index space is decoded on the device: no pair list in HBM at all
+    all_pairs_dev = None
+    if args.workload == "allpairs":
+        all_pairs_dev = gdist.shard_all_pairs(n_total, rank, world, args.block) if world > 1 else (0, n_total, 0, n_total)
+    # ---- the exchange step: records of ALL ranks in every rank's buffer, written by the kernels ----
+    gather, ep = None, None
+    n_global = n_total if args.strong else world * n_total
     if world > 1:
-        # Preferred: the gather is fused into the alignment kernel -- every finished pair stores its
-        # record into every rank's buffer over NVLink peer memory (torch symmetric memory supplies
-        # the peer mappings and the cross-rank barrier).  Fallback: NCCL all_gather after the kernel.
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            gathered = symm_mem.empty((world * B, 8), dtype=torch.float64, device=dev)
-            symm = symm_mem.rendezvous(gathered, dist.group.WORLD)
-            peer_ptrs_dev = int(symm.buffer_ptrs_dev)
-        except Exception as exc:                          # noqa: BLE001
-            print(f"[rank {rank}] symmetric memory unavailable ({exc}); using NCCL all_gather", file=sys.stderr)
-            symm = None
-            gathered = torch.empty((world * B, 8), dtype=torch.float64, device=dev)
+        if args.strong:
+            gather = gdist.FusedGather(n_global, device=dev, block=args.block)
+            ep = gather.epilogue()
+        else:                                                # rank r owns rows r*B .. (r+1)*B - 1
+            gather = gdist.FusedGather(n_global, device=dev, block=n_total)
+            ep = gather.epilogue()
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device=dev)     # 768 MB > 126 MB L2
 
-    def align_and_gather():
-        if world > 1 and symm is not None:
-            eng.run_device_gather(pairs_t, init_t, out_T, out_err, out_pass, peer_ptrs_dev, world, rank * B,
-                                  epsilon=0.05, max_iters=100)
-            symm.barrier()                                # all ranks' records have landed everywhere
-            return
-        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
-                       exhaustive=args.exhaustive)
-        if world > 1:
-            rec[:, :6] = out_T
-            rec[:, 6] = out_err
-            rec[:, 7] = out_pass.to(torch.float64)
-            dist.all_gather_into_tensor(gathered, rec)
+    def launch(exhaustive=False):
+        if exhaustive:
+            eng.run_device(None if all_pairs_dev else pairs_t, init_t, out_T, out_err, out_pass, epsilon=EPS,
+                           max_iters=MAX_ITERS, all_pairs=all_pairs_dev, exhaustive=True)
+        else:
+            eng.run_device_ex(pairs_t, init_t, out_T, out_err, out_pass, ep, epsilon=EPS, max_iters=MAX_ITERS,
+                              all_pairs=all_pairs_dev)
 
     def step_device():
-        align_and_gather()
+        launch(args.exhaustive)
+        if gather is not None:
+            gather.barrier()                                  # every rank's records have landed everywhere
 
     def barrier():
         if world > 1:
@@ -317,13 +393,35 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
+    # ---- multi-GPU correctness, outside every timed region: zeroed buffers, one step, and every block
+    # of the fused gather compared with an NCCL all_gather of the same records ----
+    gather_check = None
+    if gather is not None:
+        gather.clear()
+        step_device()
+        torch.cuda.synchronize()
+        rec = torch.empty((B, 8), dtype=torch.float64, device=dev)
+        rec[:, :6], rec[:, 6], rec[:, 7] = out_T, out_err, out_pass.to(torch.float64)
+        counts = [len(gdist.shard_indices(n_global, r, world, gather.block)) for r in range(world)]
+        cap = max(counts)
+        send = torch.zeros((cap, 8), dtype=torch.float64, device=dev)
+        send[:B] = rec
+        recv = torch.empty((world * cap, 8), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        want = torch.empty((n_global, 8), dtype=torch.float64, device=dev)
+        for r in range(world):
+            idx = torch.from_numpy(gdist.shard_indices(n_global, r, world, gather.block)).to(dev)
+            want[idx] = recv[r * cap:r * cap + counts[r]]
+        same = bool(torch.equal(gather.records(), want))
+        assert same, f"rank {rank}: the fused gather differs from the NCCL all_gather of the same records"
+        gather_check = f"fused gather == NCCL all_gather on all {n_global} rows of every rank (buffers zeroed first)"
+        barrier()
+
     launches0 = eng.launch_count
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.time()
     for k in range(args.steps):
@@ -331,91 +429,115 @@ def main():
         if world > 1:
             dist.barrier()
         ev[k][0].record()
-        if world > 1:
-            align_and_gather()
-            ev[k][1].record()
-        else:
-            eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100,
-                           exhaustive=args.exhaustive)
-            ev[k][1].record()
-        ev[k][2].record()
+        step_device()
+        ev[k][1].record()
     barrier()
     t_wall1 = time.time()
     launches = eng.launch_count - launches0
-    if world > 1:
-        # every rank must hold every rank's records: check this rank's own block and that all blocks are filled
-        mine = gathered[rank * B:(rank + 1) * B]
-        assert torch.equal(mine[:, :6], out_T) and torch.equal(mine[:, 6], out_err)
-        assert bool((gathered[:, 7] >= 1).all()), "a rank's records are missing from the gather buffer"
-    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
-    kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    step_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
     total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) * 1e-3
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
 
     # work actually done (exact: passes per pair come back from the kernel)
     passes = out_pass.cpu().numpy().astype(np.int64)
-    lens = table.lengths
-    work = float(np.sum(passes * lens[pairs[:, 0]] * lens[pairs[:, 1]]))          # PDE per step on this rank
+    work = float(np.sum(passes * lens[pairs_mine[:, 0]] * lens[pairs_mine[:, 1]]))  # PDE per step on this rank
     info = eng.kernel_info(B)
+
+    # ---- sustained segment: a few hundred milliseconds of back-to-back steps, for the clock record ----
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(20, int(0.4 / max(total_s / args.steps, 1e-4)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        for _ in range(n_sus):
+            step_device()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        sus_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sus_ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            sustained = {"steps": n_sus, "ms_per_step": float(sus_ms.item()) / n_sus,
+                         "value": (n_global if args.strong else world * B) * n_sus / (float(sus_ms.item()) * 1e-3),
+                         "l2": "not flushed (steps back to back)", "clocks": sampler.window(t0, t1)}
+
     # the same kernel with pruning switched off (every source point sweeps every target, the
-    # reference's brute force): this is the variant the FP32-pipe roofline is defined for
+    # reference's brute force): the variant the FP32-pipe roofline is defined for
     ex_ms = []
     for k in range(2 + min(args.steps, 5)):
         flush.fill_(float(k))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100, exhaustive=True)
+        launch(exhaustive=True)
         e1.record()
         torch.cuda.synchronize()
         if k >= 2:
             ex_ms.append(e0.elapsed_time(e1))
     assert np.array_equal(out_pass.cpu().numpy().astype(np.int64), passes)
     ex_s = float(np.mean(ex_ms)) * 1e-3
-    # one instrumented launch (outside every timed region): distance evaluations actually executed
+    # kernel alone (no barrier), and one instrumented launch outside every timed region: the distance
+    # evaluations actually executed
+    k_ms = []
+    for k in range(5):
+        flush.fill_(float(k))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms.append(e0.elapsed_time(e1))
+    kern_s = float(np.mean(k_ms[1:])) * 1e-3
     eng.count_work(True)
-    eng.run_device(pairs_t, init_t, out_T, out_err, out_pass, epsilon=0.05, max_iters=100)
+    launch()
     executed = float(eng.read_work())
     eng.count_work(False)
+    if gather is not None:
+        gather.barrier()
 
-    # ---- e2e: the public host API with pinned host buffers, copies inside the timed region ----
+    # ---- e2e: the public host API fed the reference's own input form, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        tab_pin = gicp.ScanTable(xy=xy_pin.numpy(), offsets=off_pin.numpy())
-        pairs_h, init_h = pairs_pin.numpy(), init
         eng2 = gicp.IcpEngine(local)
-        e2e_gathered = torch.empty((world * B, 8), dtype=torch.float64, device=dev) if world > 1 else None
-        rec_pin = torch.empty((B, 8), dtype=torch.float64).pin_memory() if world > 1 else None
-        from icp_slam_b200 import dist as gdist
+        if world > 1:
+            eng2.set_tuning("pack_threads", max(1, min(8, len(os.sched_getaffinity(0)) // 1)))
+        rec_pin = torch.empty((n_global, 8), dtype=torch.float64).pin_memory() if gather is not None else None
 
         def step_host():
-            # the public call: scans + pairs + initial guesses in host memory -> constraints in host memory
-            return eng2.align(tab_pin, pairs_h, init_h, epsilon=0.05, max_iters=100)
+            # scans (list of pageable arrays) + pairs + initial guesses in host memory -> constraints
+            # of ALL ranks in host memory
+            res = eng2.align(scans, pairs_mine, init_mine, epsilon=EPS, max_iters=MAX_ITERS, epilogue=ep)
+            if gather is not None:
+                gather.barrier()
+                rec_pin.copy_(gather.records(), non_blocking=True)
+                torch.cuda.synchronize()
+            return res
 
-        for _ in range(max(args.warmup, 1)):
+        for _ in range(max(min(args.warmup, 5), 2)):
             res = step_host()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             res = step_host()
-            if world > 1 and not os.environ.get("BENCH_E2E_NOGATHER"):   # the gather of constraint records, from host results
-                rec_pin.copy_(torch.from_numpy(gdist.pack_records(res.T, res.error, res.iters)))
-                rec.copy_(rec_pin, non_blocking=True)
-                dist.all_gather_into_tensor(e2e_gathered, rec)
-                # finish the collective before the next step's kernel (whose CTAs wait on the copy
-                # engine) takes the SMs: kernels of different ranks must never wait on each other
-                torch.cuda.synchronize()
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        h2d = table.xy.nbytes + table.offsets.nbytes + pairs.nbytes + init6.nbytes
-        d2h = B * (6 * 8 + 8 + 4)
-        e2e = {"value": world * B * args.steps / float(t_e2e.item()), "unit": UNIT,
+        h2d = table.xy.nbytes + table.offsets.nbytes + pairs_mine.nbytes + (0 if init_mine is None else B * 48) + 4 * B
+        d2h = B * (6 * 8 + 8 + 4) + 4 + (0 if gather is None else n_global * 64)
+        e2e = {"value": (n_global if args.strong else world * B) * args.steps / float(t_e2e.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(t_e2e.item()) / args.steps * 1e3}
+               "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
+               "input": "lidar_points as the reference holds them: a Python list of separate pageable (m_i, 2) "
+                        "float64 arrays, packed into pinned staging by the library's host threads while earlier "
+                        "pieces are on the wire",
+               "call": "IcpEngine.align -> icpb_align_host_scans" + ("" if gather is None else
+                       " with the fused-gather epilogue, symmetric-memory barrier, D2H of all ranks' records")}
         assert np.array_equal(res.iters, passes.astype(np.int32))
         eng2.close()
 
@@ -429,63 +551,74 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         sm_count = info["sm_count"]
-        kern_s = float(kern_ms.mean()) * 1e-3
-        pde_peak = sm_count * 128 * sm_max_mhz * 1e6 / 4.0                 # FP32-pipe slots / 4 per PDE
-        achieved = work / kern_s
-        alg_bytes = float(np.sum(16.0 * (lens[pairs[:, 0]] + lens[pairs[:, 1]]) + 60.0 + 56.0))
+        pde_peak = sm_count * 128 * sm_max_mhz * 1e6 / 4.0                 # FP32-pipe lane-slots / 4 per PDE
+        ncu = None
+        try:
+            ncu = json.load(open(NCU_SUMMARY))
+        except (OSError, ValueError):
+            pass
+        same_wl = bool(ncu) and ncu.get("workload") == args.workload and ncu.get("scans") == args.scans \
+            and ncu.get("beams") == args.beams and world == 1
+        alg_bytes = float(np.sum(16.0 * (lens[pairs_mine[:, 0]] + lens[pairs_mine[:, 1]]) + 60.0 + 56.0))
         roofline = {
-            "bound": "fp32_pipe", "achieved": achieved * 1e-12, "peak": pde_peak * 1e-12, "unit": "TPDE/s",
-            "frac": achieved / pde_peak, "traffic": TRAFFIC_NCU,
-            "note": "achieved counts ALGORITHMIC distance evaluations (passes*N1*N2); the product kernel "
-                    "proves most of them unnecessary (exact chunk pruning) and executes only "
-                    "executed_share of them, so frac can exceed 1; `exhaustive` is the same kernel "
-                    "with pruning off, the variant the pipe roofline bounds",
+            "bound": "fp32_pipe", "unit": "TPDE/s",
+            "achieved": executed / kern_s * 1e-12, "peak": pde_peak * 1e-12, "frac": executed / kern_s / pde_peak,
+            "traffic": (ncu or {}).get("dram_bytes") if same_wl else None,
+            "definition": "PDE = one point-pair distance evaluation = 4 FP32-pipe lane-slots (FADD, FADD, FMUL, FFMA); "
+                          "peak = SMs*128*sm_max_mhz/4 (clock " + peak_src + "); achieved = distance evaluations the "
+                          "timed kernel EXECUTED (counted by an instrumented launch of the same kernel) / its "
+                          "average duration; frac = the share of the FP32 pipe's lane-slots it used",
+            "kernel_ms": kern_s * 1e3, "executed_pde_per_launch": executed,
+            "algorithmic": {"pde_per_launch": work, "executed_share": executed / work,
+                            "speedup_over_exhaustive_sweep": ex_s / kern_s,
+                            "note": "passes*N1*N2 is what the reference's brute force evaluates; exact chunk pruning "
+                                    "proves the rest unnecessary (bit-identical results, tests/test_gpu_parity.py)"},
             "exhaustive": {"kernel_ms": ex_s * 1e3, "achieved": work / ex_s * 1e-12, "frac": work / ex_s / pde_peak,
-                           "pairs_per_s": B / ex_s},
-            "definition": "PDE = one point-pair distance evaluation = 4 FP32-pipe lane-slots (FADD,FADD,FMUL,FFMA); "
-                          "peak = SMs*128*sm_max_mhz/4 (SURVEY.md 8d formula; clock " + peak_src + ")",
-            "pde_per_launch": work, "kernel_ms": kern_s * 1e3,
-            "executed_pde_per_launch": executed, "executed_share": executed / work,
-            "executed_frac_of_peak": executed / kern_s / pde_peak,
-            "flops_view": {"achieved_tflops": achieved * 5e-12, "fma_peak_tflops": sm_count * 128 * 2 * sm_max_mhz * 1e-6},
+                           "pairs_per_s": B / ex_s,
+                           "note": "the same kernel with pruning off: every distance executed, the variant the "
+                                   "FP32-pipe roofline bounds; with the min tree on the ALU pipe (which does not "
+                                   "overlap with packed f32x2 instructions, profiles/r02_micro_pipes.log) the "
+                                   "attainable fraction is 0.80"},
             "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kern_s * 1e-9,
                          "peak_gbs": hbm_peak, "frac": alg_bytes / kern_s * 1e-9 / hbm_peak, "peak_source": peak_src},
         }
-        if args.workload == "chain" and args.scans == 5000 and args.beams == 1024:
-            # what actually bounds the pruned kernel: warp-instruction issue slots (4 schedulers per SM,
-            # one instruction per cycle each); the instruction count is the ncu figure of this launch
-            roofline["issue_view"] = {
-                "warp_instructions_per_launch": WARP_INSTR_NCU,
-                "frac_of_issue_peak": WARP_INSTR_NCU / (kern_s * sm_count * 4 * sm_max_mhz * 1e6),
-                "source": "smsp__inst_executed.sum, profiles/r01m_align_ncu_full_summary.csv"}
+        if same_wl:
+            # what bounds the pruned kernel: pipe-weighted issue cycles (packed f32x2, ALU-pipe and fp64
+            # instructions hold their pipe two cycles); counters of a committed capture of this command
+            roofline["issue_view"] = {k: ncu[k] for k in ("warp_instructions", "pipe_weighted_cycles_per_smsp",
+                                                          "kernel_cycles_elapsed", "frac_of_weighted_issue_peak",
+                                                          "source", "commit") if k in ncu}
         cpu = None
         if world == 1 and not args.no_cpu:
             if _ALL_CPUS:
                 os.sched_setaffinity(0, _ALL_CPUS)            # the CPU baseline gets every host core back
             rate, nthr, n, dt, mean_pass = cpu_port_rate(scans, pairs, init, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
-                   "sample": f"{n} of {B} chain pairs (seeded random subsample) in {dt:.1f} s, "
-                             f"mean {mean_pass:.1f} passes, C port oracle/icp_oracle.c on {nthr} threads"}
+                   "sample": f"{n} of {n_total} pairs (seeded random subsample) in {dt:.1f} s, "
+                             f"mean {mean_pass:.1f} passes, C port oracle/icp_oracle.c on {nthr} threads",
+                   "numpy_reference": numpy_reference_rate(scans, pairs, init, args.cpu_seconds)}
+        pairs_per_step = n_global if args.strong else world * B
         line = {
-            "metric": METRIC, "value": world * B * args.steps / total_s, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": pairs_per_step * args.steps / total_s, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"{args.label}, {B} pairs per GPU per step",
-                       "pairs_per_step": world * B, "epsilon": 0.05, "max_iters": 100,
-                       "mean_passes": float(passes.mean()), "l2": "flushed between timed steps (768 MB fill)",
-                       "collective": ("none" if world == 1 else
-                                      "fused: kernel epilogue stores (B,8) f64 records into every rank's buffer over "
-                                      "NVLink peer memory + symmetric-memory barrier" if symm is not None else
-                                      "NCCL all_gather of (B,8) f64 constraint records"),
-                       "kernel": info, "host_affinity": numa},
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_of(args, world),
+            "details": {"pairs_per_step": pairs_per_step, "pairs_per_gpu": B, "mean_passes": float(passes.mean()),
+                        "collective": ("none" if world == 1 else
+                                       "fused: kernel epilogue stores (pairs, 8) f64 records into every rank's buffer "
+                                       "over NVLink peer memory at their global rows + symmetric-memory barrier"),
+                        "partition": ("one GPU" if world == 1 else
+                                      f"interleaved blocks of {args.block} problems" if args.strong else
+                                      "every rank its own chain"),
+                        "gather_check": gather_check, "kernel": info, "host_affinity": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "sustained": sustained,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    sampler.stop()
     if world > 1:
         dist.destroy_process_group()
 

@@ -14,6 +14,9 @@
 #include <condition_variable>
 #include <time.h>
 #include <sched.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "icpb.h"
 #include "icpb_kernels.cuh"
@@ -155,6 +158,49 @@ struct PackJob {
     std::atomic<uint64_t> bad{0};       // non-finite coordinate seen
 };
 
+// One scan into the pinned staging table with NON-TEMPORAL stores, checking for inf / NaN on the way.
+// Ordinary stores leave the freshly written lines dirty in the writing core's private cache; the
+// copy engine's reads then have to snoop them out of cores that have already gone idle, and the
+// last pieces of the table -- the ones still cache resident when the packing ends -- crawl at
+// ~8 GB/s instead of 55 (measured: the last two 5 MB pieces took 0.43 and 0.85 ms against 0.10 ms
+// for the others).  Streaming stores go to memory through the write-combining buffers and skip
+// the read-for-ownership as well.
+static inline uint64_t copy_scan(double *dst, const double *src, int64_t n_doubles)
+{
+    uint64_t bad = 0;
+#if defined(__x86_64__)
+    const __m128i expo = _mm_set_epi32(0x7ff00000, 0, 0x7ff00000, 0);       // exponent bits of both doubles
+    __m128i acc = _mm_setzero_si128();
+    int64_t k = 0;
+    for (; k + 8 <= n_doubles; k += 8) {                                    // one 64-byte line per trip
+        const __m128d a = _mm_loadu_pd(src + k), b = _mm_loadu_pd(src + k + 2);
+        const __m128d c = _mm_loadu_pd(src + k + 4), d = _mm_loadu_pd(src + k + 6);
+        _mm_stream_pd(dst + k, a); _mm_stream_pd(dst + k + 2, b);
+        _mm_stream_pd(dst + k + 4, c); _mm_stream_pd(dst + k + 6, d);
+        // all-ones exponent = inf or NaN: compare the high words, ignore the low ones
+        const __m128i ea = _mm_cmpeq_epi32(_mm_and_si128(_mm_castpd_si128(a), expo), expo);
+        const __m128i eb = _mm_cmpeq_epi32(_mm_and_si128(_mm_castpd_si128(b), expo), expo);
+        const __m128i ec = _mm_cmpeq_epi32(_mm_and_si128(_mm_castpd_si128(c), expo), expo);
+        const __m128i ed = _mm_cmpeq_epi32(_mm_and_si128(_mm_castpd_si128(d), expo), expo);
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(ea, eb), _mm_or_si128(ec, ed)));
+    }
+    for (; k + 2 <= n_doubles; k += 2) {
+        const __m128d a = _mm_loadu_pd(src + k);
+        _mm_stream_pd(dst + k, a);
+        acc = _mm_or_si128(acc, _mm_cmpeq_epi32(_mm_and_si128(_mm_castpd_si128(a), expo), expo));
+    }
+    // the low words compare equal trivially (0 == 0): keep the high words only
+    const __m128i hi = _mm_and_si128(acc, _mm_set_epi32(-1, 0, -1, 0));
+    bad = (uint64_t)(_mm_movemask_epi8(hi) != 0);
+#else
+    memcpy(dst, src, sizeof(double) * (size_t)n_doubles);
+    const uint64_t *u = (const uint64_t *)dst;
+    for (int64_t k = 0; k < n_doubles; ++k)
+        bad |= (uint64_t)((u[k] & 0x7ff0000000000000ULL) == 0x7ff0000000000000ULL);
+#endif
+    return bad;
+}
+
 static void pack_run(PackJob *job)
 {
     for (;;) {
@@ -163,14 +209,11 @@ static void pack_run(PackJob *job)
         uint64_t bad = 0;
         for (int64_t s = job->job_first[j]; s < job->job_last[j]; ++s) {
             const int64_t o = job->offsets[s], m = job->offsets[s + 1] - o;
-            const double *src = job->scan_xy[s];
-            double *d = job->dst + 2 * o;
-            memcpy(d, src, sizeof(double) * 2 * (size_t)m);
-            // finiteness check on the copy (cache-resident): all-ones exponent = inf or NaN
-            const uint64_t *u = (const uint64_t *)d;
-            for (int64_t k = 0; k < 2 * m; ++k)
-                bad |= (uint64_t)((u[k] & 0x7ff0000000000000ULL) == 0x7ff0000000000000ULL);
+            bad |= copy_scan(job->dst + 2 * o, job->scan_xy[s], 2 * m);
         }
+#if defined(__x86_64__)
+        _mm_sfence();                                   // the streamed lines are in memory before the piece is announced
+#endif
         if (bad) job->bad.fetch_or(1, std::memory_order_relaxed);
         job->done[job->job_piece[j]].fetch_add(1, std::memory_order_release);
     }
@@ -238,6 +281,7 @@ struct PackPool {
 struct icpb_ctx {
     int device = 0;
     int sm_count = 0;
+    int smem_limit = 0;                             // dynamic shared memory an alignment launch may ask for
     // scan table
     const double *xy = nullptr;
     const int64_t *offsets = nullptr;
@@ -265,10 +309,9 @@ struct icpb_ctx {
     DevBuf s_accept;                                // acceptance epilogue: [appended, CTAs left] counters
     PinnedBuf stage_xy;                             // pinned copy of a scan table packed from a list of arrays
     PackPool *pool = nullptr;                       // host threads that pack scans into stage_xy
-    int max_smem_set = 0;
     // tuning / test hooks (icpb_set_tuning); 0 or -1 = the library's own choice
     int tune_threads = 0, tune_cluster = -1, tune_segments = 0, tune_sgd_cluster = 0, tune_pack_threads = 0;
-    bool tune_flag_copy = false, tune_drop_counter = false, tune_trace = false;
+    bool tune_flag_copy = false, tune_drop_counter = false, tune_trace = false, tune_prepack = false;
 };
 
 namespace {
@@ -289,9 +332,9 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     if (threads < 32) threads = 32;
     const icpb::SmemLayout L = icpb::smem_layout(longest, threads / 32);
     const int64_t smem = L.bytes;
-    if (smem > kMaxSmem) {
+    if (smem > h->smem_limit) {
         snprintf(g_err, sizeof g_err, "scan of %lld points needs %lld B of shared memory (limit %d)",
-                 (long long)longest, (long long)smem, kMaxSmem);
+                 (long long)longest, (long long)smem, h->smem_limit);
         return ICPB_ETOOLONG;
     }
     c->threads = threads; c->smem = (int)smem; c->L = L;
@@ -312,15 +355,8 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
         if (v == 0 || v == 1) c->cluster = 1;
         else if ((v == 2 || v == 4 || v == 8) && fn == pick_kernel(nullptr)) c->cluster = v;
     }
-    if ((int)smem > h->max_smem_set) {
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsExhaustive, false, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(icpb::icp_align_kernel<kPointsPerThread, true, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->max_smem_set = (int)smem;
-    }
+    // (the kernels' dynamic shared-memory limit is raised to the device maximum once, in icpb_create: the
+    // attribute belongs to the function, not to a handle, so it must not follow one handle's history)
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     if (per_sm < 1) return fail(ICPB_EINVAL, "kernel does not fit on an SM%s");
@@ -471,6 +507,18 @@ int icpb_create(int device, icpb_handle *out)
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&h->cstream[k], cudaStreamNonBlocking);
     for (int k = 0; k < 16 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->seg_ev[k], cudaEventDisableTiming);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->done_ev[k], cudaEventDisableTiming);
+    // dynamic shared memory up to the device's opt-in maximum minus each kernel's static part, set
+    // once: the attribute belongs to the function, not to a handle
+    h->smem_limit = (int)prop.sharedMemPerBlockOptin;
+    for (kernel_fn fn : {pick_kernel(nullptr), cluster_kernel(),
+                         (kernel_fn)icpb::icp_align_kernel<kPointsExhaustive, false, false>}) {
+        cudaFuncAttributes fa;
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) break;
+        const int lim = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        if (lim < h->smem_limit) h->smem_limit = lim;
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->arrived_dev, sizeof(int32_t));
     if (e == cudaSuccess) e = cudaHostAlloc(&h->seg_vals_pinned, sizeof(int32_t) * (kMaxSegments + 1), cudaHostAllocDefault);
     if (e == cudaSuccess) for (int k = 0; k <= kMaxSegments; ++k) h->seg_vals_pinned[k] = k;
@@ -507,6 +555,7 @@ int icpb_set_tuning(icpb_handle h, const char *key, int64_t value)
     else if (!strcmp(key, "flag_copy")) h->tune_flag_copy = v != 0;
     else if (!strcmp(key, "drop_counter")) h->tune_drop_counter = v != 0;
     else if (!strcmp(key, "trace")) h->tune_trace = v != 0;
+    else if (!strcmp(key, "prepack")) h->tune_prepack = v != 0;
     else return fail(ICPB_EINVAL, "icpb_set_tuning: unknown key %s", key);
     return 0;
 }
@@ -707,12 +756,25 @@ int icpb_plan_upload(const int64_t *h_offsets, int64_t n_scans, int32_t pieces_w
     const size_t nb_xy = sizeof(double) * 2 * (size_t)total;
     int nseg = (int)(nb_xy / (4u << 20)) + 1;
     if (nseg > 16) nseg = 16;
+    // Default plan: the first two and the last two pieces are a quarter and a half of a standard
+    // piece, so the first bytes are on the wire (and the first pairs running) sooner and fewer pairs
+    // are left waiting for the last piece.  An explicit piece count gives equal pieces.
+    const bool graded = !(pieces_wanted >= 1 && pieces_wanted <= kMaxSegments) && nseg >= 8;
+    if (graded) nseg += 2;
     if (pieces_wanted >= 1 && pieces_wanted <= kMaxSegments) nseg = pieces_wanted;
     if (nseg > n_scans) nseg = (int)n_scans;
+    double cum[kMaxSegments + 1];
+    cum[0] = 0.0;
+    for (int k = 0; k < nseg; ++k) {
+        double w = 1.0;
+        if (graded && (k == 0 || k == nseg - 1)) w = 0.25;
+        if (graded && (k == 1 || k == nseg - 2)) w = 0.5;
+        cum[k + 1] = cum[k] + w;
+    }
     int64_t s = 0;
     int made = 0;
     for (int k = 0; k < nseg - 1; ++k) {
-        const int64_t want = total * (k + 1) / nseg;
+        const int64_t want = (int64_t)((double)total * (cum[k + 1] / cum[nseg]));
         while (s < n_scans && h_offsets[s] < want) ++s;
         int64_t pick = -1;
         for (int64_t c = s; c < n_scans && c < s + 64; ++c) {
@@ -834,7 +896,8 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
     const double *up_xy = src.xy;
     if (src.scan_xy) {
         int nthr = h->tune_pack_threads > 0 ? h->tune_pack_threads : host_threads_available();
-        if (nthr > 8) nthr = 8;
+        if (nthr > 32) nthr = 32;
+        if (h->tune_pack_threads <= 0 && nthr > 8) nthr = 8;      // default: at most 8
         if (nthr < 1) nthr = 1;
         if (!h->pool && nthr > 1) h->pool = new (std::nothrow) PackPool(nthr - 1);
         jobs_of_piece.assign((size_t)nseg, 0);
@@ -959,7 +1022,12 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
                 d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, ep,
                 in_order ? nullptr : d_order, d_passes + B);
     if (rc) { pack_finish(); return align_abort(h, rc); }
+    if (src.scan_xy && h->tune_prepack) { pack_run(&job); if (h->pool) h->pool->finish(); }   // experiment: no overlap
     bool bad_scans = false;
+    double t_ready[kMaxSegments] = {0}, t_enqd[kMaxSegments] = {0};   // trace: piece k packed / enqueued (host clock)
+    cudaEvent_t tev[kMaxSegments + 1] = {nullptr};            // trace: when piece k had landed (device clock)
+    cudaEvent_t tev0[kMaxSegments] = {nullptr};               // trace: when piece k's copy could start
+    if (trace) { cudaEventCreate(&tev[kMaxSegments]); cudaEventRecord(tev[kMaxSegments], cp); }
     for (int k = n_sent; k < nseg; ++k) {
         if (src.scan_xy) {
             // this thread packs too while a piece is incomplete (pack_run returns when no job is left)
@@ -976,7 +1044,9 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
             }
             if (job.bad.load(std::memory_order_relaxed)) { bad_scans = true; break; }
         }
+        if (trace) { t_ready[k] = now_us() - t_entry; cudaEventCreate(&tev0[k]); cudaEventRecord(tev0[k], cp); }
         CUP(enqueue_piece(k));
+        if (trace) { t_enqd[k] = now_us() - t_entry; cudaEventCreate(&tev[k]); cudaEventRecord(tev[k], cp); }
     }
     pack_finish();
     if (bad_scans) {
@@ -1012,9 +1082,19 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
     }
     memcpy(h_err, tE, nbE);
     memcpy(h_passes, tP, nb4);
-    if (trace)
+    if (trace) {
         fprintf(stderr, "[icpb_align_host] prep %.0f us, enqueue %.0f us, wait %.0f us, scatter %.0f us (%d segments)\n",
                 t_prep - t_entry, t_enq - t_prep, t_sync - t_enq, now_us() - t_sync, nseg);
+        fprintf(stderr, "  piece: packed at / enqueued at (host us) / landed at (us after the copy stream's first event):");
+        for (int k = 0; k < nseg; ++k) {
+            float ms = 0.f, ms0 = 0.f;
+            if (tev[k]) { cudaEventElapsedTime(&ms, tev[kMaxSegments], tev[k]); cudaEventDestroy(tev[k]); }
+            if (tev0[k]) { cudaEventElapsedTime(&ms0, tev[kMaxSegments], tev0[k]); cudaEventDestroy(tev0[k]); }
+            fprintf(stderr, " %d:%.0f/%.0f/%.0f-%.0f", k, t_ready[k], t_enqd[k], ms0 * 1e3, ms * 1e3);
+        }
+        fprintf(stderr, "\n");
+        cudaEventDestroy(tev[kMaxSegments]);
+    }
     return 0;
 #undef CUP
 }

@@ -537,3 +537,166 @@ def test_fused_gather_epilogue_many_peers(gicp, n_peers):
         np.testing.assert_array_equal(got[:, 6], ref.error)
         np.testing.assert_array_equal(got[:, 7], ref.iters)
     e.close()
+
+
+def test_short_scans_many_peers_and_row_map(gicp):
+    """Scans of <= 64 points run in 32-thread CTAs: the epilogue must still serve 8 peers (it loops
+    over the 64 record words), and the row map must place local problem b at
+    row0 + (b // block) * stride + b % block -- the interleaved-block partition of dist.shard_indices."""
+    import torch
+    from icp_slam_b200 import dist as gdist, synth
+    rng = np.random.default_rng(5)
+    poses = synth.loop_trajectory(50, step=0.05)
+    scans = synth.scans_from_poses(poses, 48, rng)
+    n_total, world, block = 1100, 4, 64
+    allp = np.stack((rng.integers(0, 50, n_total), rng.integers(0, 50, n_total)), axis=1).astype(np.int32)
+    e = gicp.IcpEngine()
+    e.set_scans(scans)
+    ref = e.run(allp, None, epsilon=0.05, max_iters=20)
+    assert e.kernel_info(n_total)["threads_per_cta"] == 32
+    dev = torch.device("cuda", e.device)
+    bufs = [torch.full((n_total, 8), -1.0, dtype=torch.float64, device=dev) for _ in range(8)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    for rank in range(world):                                  # the ranks of a 4-GPU job, one after the other
+        mine = gdist.shard_indices(n_total, rank, world, block)
+        row0, rb, rs = gdist.global_rows(n_total, rank, world, block)
+        B = len(mine)
+        pairs_t = torch.from_numpy(np.ascontiguousarray(allp[mine])).to(dev)
+        oT = torch.empty((B, 6), dtype=torch.float64, device=dev)
+        oe = torch.empty(B, dtype=torch.float64, device=dev)
+        op = torch.empty(B, dtype=torch.int32, device=dev)
+        ep = gicp.make_epilogue(ptrs.data_ptr(), 8, rank, row0, rb, rs)
+        e.run_device_ex(pairs_t, None, oT, oe, op, ep, epsilon=0.05, max_iters=20)
+    torch.cuda.synchronize()
+    for b in bufs:                                             # every peer holds every record, in global order
+        got = b.cpu().numpy()
+        np.testing.assert_array_equal(got[:, :6].reshape(-1, 2, 3), ref.T[:, :2, :])
+        np.testing.assert_array_equal(got[:, 6], ref.error)
+        np.testing.assert_array_equal(got[:, 7], ref.iters)
+    e.close()
+
+
+def test_acceptance_epilogue_compacts_on_the_device(gicp):
+    """the callers' `error < thresh` test (src/loop_closure_detection.py:35-39, 155-159)
+    and the compaction run in the kernel epilogue; the accepted records equal the host filter's, once
+    ordered by the pair id they carry."""
+    import torch
+    from icp_slam_b200 import dist as gdist, synth
+    rng = np.random.default_rng(12)
+    poses = synth.loop_trajectory(120, step=0.25)
+    scans = synth.scans_from_poses(poses, 360, rng, drop_frac=0.03)
+    ij = synth.all_pairs_decode(np.arange(synth.all_pairs_count(120)), 120)
+    pairs = np.stack((ij[:, 1], ij[:, 0]), axis=1).astype(np.int32)[::3]
+    e = gicp.IcpEngine()
+    e.set_scans(scans)
+    ref = e.run(pairs, None, epsilon=0.05, max_iters=60)
+    thresh = float(np.median(ref.error))
+    keep = np.nonzero(ref.error < thresh)[0]
+    assert 10 < len(keep) < len(pairs) - 10
+    dev = torch.device("cuda", e.device)
+    B = len(pairs)
+    pairs_t = torch.from_numpy(pairs).to(dev)
+    oT = torch.empty((B, 6), dtype=torch.float64, device=dev)
+    oe = torch.empty(B, dtype=torch.float64, device=dev)
+    op = torch.empty(B, dtype=torch.int32, device=dev)
+    for cap in (B, len(keep) - 5):
+        rec = torch.zeros((max(cap, 1), 8), dtype=torch.float64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        ep = gicp.make_epilogue(accept_thresh=thresh, accept_rec=rec.data_ptr(), accept_count=cnt.data_ptr(),
+                                accept_cap=cap, row0=1000)
+        e.run_device_ex(pairs_t, None, oT, oe, op, ep, epsilon=0.05, max_iters=60)
+        torch.cuda.synchronize()
+        n = int(cnt.item())
+        if cap < len(keep):
+            assert n == -len(keep)                             # overflow is reported, nothing written past the cap
+            continue
+        assert n == len(keep)
+        rows, T, err, passes = gdist.unpack_accepted(rec[:n].cpu().numpy())
+        np.testing.assert_array_equal(rows, keep + 1000)
+        np.testing.assert_array_equal(T, ref.T[keep])
+        np.testing.assert_array_equal(err, ref.error[keep])
+        np.testing.assert_array_equal(passes, ref.iters[keep])
+    np.testing.assert_array_equal(oe.cpu().numpy(), ref.error)  # the plain outputs are written as always
+    e.close()
+
+
+def test_list_of_arrays_equals_packed_table(gicp):
+    """The reference's own input form -- a list of separate pageable (m_i, 2) arrays -- goes through
+    icpb_align_host_scans (host threads pack into pinned staging while the upload runs) and gives the
+    bits of the packed-table path; odd elements (float32, Fortran order, lists) are converted."""
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(900, 720, seed=15)
+    e = gicp.IcpEngine()
+    want = e.align(gicp.ScanTable(scans), pairs, init, epsilon=0.05, max_iters=30)
+    for nthr in (1, 3, 8):
+        e.set_tuning("pack_threads", nthr)
+        got = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
+        np.testing.assert_array_equal(got.T, want.T)
+        np.testing.assert_array_equal(got.error, want.error)
+        np.testing.assert_array_equal(got.iters, want.iters)
+    e.set_tuning("pack_threads", 0)
+    assert e.table.n_scans == len(scans) and e.table.longest == max(len(s) for s in scans)
+    b = e.run(pairs[:50], init[:50], epsilon=0.05, max_iters=30)        # the uploaded table stays resident
+    np.testing.assert_array_equal(b.T, want.T[:50])
+    odd = list(scans)
+    odd[3] = np.asfortranarray(scans[3])
+    odd[4] = scans[4].tolist()
+    odd[5] = scans[5].astype(np.float32).astype(np.float64)[::1]
+    ref5 = e.align(gicp.ScanTable(odd), pairs[:20], init[:20], epsilon=0.05, max_iters=30)
+    got5 = e.align(odd, pairs[:20], init[:20], epsilon=0.05, max_iters=30)
+    np.testing.assert_array_equal(got5.T, ref5.T)
+    got_t = e.align(tuple(scans), pairs[:20], init[:20], epsilon=0.05, max_iters=30)
+    np.testing.assert_array_equal(got_t.T, want.T[:20])
+    e.close()
+
+
+def test_list_upload_rejects_non_finite_scans_midway(gicp):
+    """A NaN in a late scan is found by the packing threads while earlier pieces are already on the
+    device and the kernel is waiting: the call must come back with ValueError (no hang), leave the
+    handle without a table, and the next call must work."""
+    from icp_slam_b200 import synth
+    scans, pairs, init, _, _ = synth.make_chain_workload(900, 720, seed=16)
+    e = gicp.IcpEngine()
+    good = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
+    bad = list(scans)
+    bad[700] = scans[700].copy()
+    bad[700][33, 1] = np.nan
+    with pytest.raises(ValueError, match="non-finite"):
+        e.align(bad, pairs, init, epsilon=0.05, max_iters=30)
+    assert e.table is None
+    with pytest.raises(ValueError):
+        e.run(pairs[:4], init[:4])                              # no table: nothing stale is used
+    bad[700][33, 1] = np.inf
+    with pytest.raises(ValueError, match="non-finite"):
+        e.align(bad, pairs, init, epsilon=0.05, max_iters=30)
+    again = e.align(scans, pairs, init, epsilon=0.05, max_iters=30)
+    np.testing.assert_array_equal(again.T, good.T)
+    with pytest.raises(ValueError):
+        e.align(scans[:10] + [np.zeros((0, 2))], pairs[:3], init[:3])
+    e.close()
+
+
+def test_single_target_fit_is_the_identity_rotation(gicp, c_oracle):
+    """Every source point matched to ONE target: the centred target cloud is zero and the SVD of a zero
+    covariance gives the identity rotation (SURVEY probe B5).  The reference only gets there when its
+    mean of N copies rounds to the value itself -- otherwise its rotation is rounding noise -- so the
+    kernel decides the case exactly.  Pass counts and errors do not depend on that rotation and must
+    equal the oracle's; the translation must put the source centroid on the target."""
+    rng = np.random.default_rng(77)
+    for n1 in (1, 2, 5, 64, 65, 333, 1500):
+        src = rng.normal(0, 3, size=(n1, 2))
+        dst = rng.normal(0, 3, size=(1, 2))
+        res = gicp.icp_batch([src, dst], np.array([[0, 1]], dtype=np.int32), None, return_history=True)
+        T, err, passes, _ = c_oracle.icp_pair(src, dst, None)
+        assert res.iters[0] == passes
+        np.testing.assert_allclose(res.error[0], err, rtol=1e-9, atol=1e-18)
+        for k in range(passes):
+            np.testing.assert_array_equal(res.history[0, k, :2, :2], np.eye(2))      # exactly the identity
+        np.testing.assert_allclose(res.history[0, 0, :2, 2], dst[0] - src.mean(axis=0), atol=1e-12)
+    # far-apart clouds: the first passes match everything to one extremal target, later ones do not
+    src = rng.normal(0, 1, size=(200, 2)) + [40.0, 0.0]
+    dst = rng.normal(0, 1, size=(300, 2))
+    a = gicp.icp_batch([src, dst], np.array([[0, 1]], dtype=np.int32), None, return_history=True,
+                       return_correspondences=True)
+    b = gicp.engine().run(np.array([[0, 1]], dtype=np.int32), None, return_history=True, exhaustive=True)
+    np.testing.assert_array_equal(a.history, b.history)

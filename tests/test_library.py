@@ -140,10 +140,53 @@ def test_upload_plan_pieces_end_on_sector_boundaries():
         assert e[-1] == n and np.all(np.diff(e) > 0) and e[0] >= 1
         assert np.all(off[e[:-1]] % 2 == 0)                      # interior boundaries: even point offsets
         if want == 0:
-            assert k.value <= 16
-    # a table of 5,000 x 1,024-point scans: 16 pieces, all on 128-byte lines
+            assert k.value <= 18
+    # a table of 5,000 x 1,024-point scans: 18 pieces (the first and last two a quarter and a half of
+    # a standard one, so the upload starts and ends with short pieces), all on 128-byte lines
     off = (np.arange(5001) * 1024).astype(np.int64)
     ends = np.zeros(64, dtype=np.int64); k = ctypes.c_int32()
     assert L.icpb_plan_upload(off.ctypes.data, 5000, 0, ends.ctypes.data, ctypes.byref(k)) == 0
-    assert k.value == 16 and np.all(off[ends[:15]] % 8 == 0)
+    assert k.value == 18 and np.all(off[ends[:17]] % 8 == 0)
+    sizes = np.diff(np.concatenate(([0], ends[:18])))
+    assert sizes[0] < sizes[1] < sizes[2] and sizes[-1] < sizes[-2] < sizes[-3]
+    assert L.icpb_plan_upload(off.ctypes.data, 5000, 16, ends.ctypes.data, ctypes.byref(k)) == 0
+    assert k.value == 16 and np.ptp(np.diff(np.concatenate(([0], ends[:16])))) <= 1       # explicit count: equal pieces
     assert L.icpb_plan_upload(None, 5000, 0, ends.ctypes.data, ctypes.byref(k)) != 0
+
+
+def test_epilogue_struct_layout_matches_header():
+    """icpb_epilogue as ctypes sees it: 12 fields, 88 bytes, in the header's order."""
+    from icp_slam_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "icpb.h")).read()
+    body = re.search(r"typedef struct icpb_epilogue \{(.*?)\} icpb_epilogue;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for decl in body.split(";") for n in re.findall(r"\*?\s*(\w+)\s*(?:,|$)", decl.split(None, 1)[1] if decl.split() else "")
+             if n not in ("const", "uint64_t", "int32_t", "int64_t", "double")]
+    assert names == [n for n, _ in _lib.IcpbEpilogue._fields_]
+    assert ctypes.sizeof(_lib.IcpbEpilogue) == 88
+
+
+def test_scan_list_helper_describes_a_list_of_arrays():
+    """ScanList: pointer + length per scan straight from the caller's arrays (buffer protocol helper,
+    no copies), conversions only for elements that are not C-ordered float64."""
+    from icp_slam_b200 import icp as gicp
+    rng = np.random.default_rng(0)
+    scans = [rng.normal(size=(int(m), 2)) for m in rng.integers(1, 400, size=257)]
+    sl = gicp.ScanList(scans)
+    assert sl.keep is scans and sl.n_scans == 257
+    np.testing.assert_array_equal(sl.lens, [len(s) for s in scans])
+    np.testing.assert_array_equal(sl.ptrs, [s.ctypes.data for s in scans])
+    odd = list(scans)
+    odd[10] = np.asfortranarray(scans[10])
+    odd[200] = scans[200].astype(np.float32)
+    so = gicp.ScanList(odd)
+    assert so.keep is not odd and so.ptrs[9] == scans[9].ctypes.data and so.ptrs[10] != odd[10].ctypes.data
+    np.testing.assert_array_equal(so.keep[200], scans[200].astype(np.float32).astype(np.float64))
+    with pytest.raises(ValueError):
+        gicp.ScanList(scans[:3] + [np.zeros((0, 2))])
+    with pytest.raises(ValueError):
+        gicp.ScanList(scans[:3] + [np.zeros((5, 3))])
+    with pytest.raises(ValueError):
+        gicp.ScanList([])
+    t = gicp.ScanTable.from_lengths(sl.lens)
+    assert t.n_scans == 257 and t.longest == int(sl.lens.max())

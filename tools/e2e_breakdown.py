@@ -15,7 +15,7 @@ def tm(f, n=10):
 print("align (pinned scans)      %.3f ms" % tm(lambda: e.align(tp, pairs, init, epsilon=0.05)))
 print("align (pageable table)    %.3f ms" % tm(lambda: e.align(t, pairs, init, epsilon=0.05)))
 # the reference's own input form: a list of separate pageable (m_i, 2) arrays (src/dataloader.py:110-112)
-for nthr in (1, 2, 4, 8):
+for nthr in (4, 8, 12, 16):
     e.set_tuning("pack_threads", nthr)
     print("align (list, %d pack thr)  %.3f ms" % (nthr, tm(lambda: e.align(scans, pairs, init, epsilon=0.05))))
 e.set_tuning("pack_threads", 0)
