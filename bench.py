@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     ap.add_argument("--no-sustained", action="store_true", help="skip the sustained-clock segment")
+    ap.add_argument("--no-exhaustive", action="store_true", help="skip the pruning-off launches (long workloads)")
     args = ap.parse_args()
     dflt = {"chain": (5000, 1024), "proximity": (5000, 1024), "allpairs": (600, 1024), "highres": (48, 4096)}
     args.scans = args.scans or dflt[args.workload][0]
@@ -470,7 +471,7 @@ def main():
     # the same kernel with pruning switched off (every source point sweeps every target, the
     # reference's brute force): the variant the FP32-pipe roofline is defined for
     ex_ms = []
-    for k in range(2 + min(args.steps, 5)):
+    for k in range(0 if args.no_exhaustive else 2 + min(args.steps, 5)):
         flush.fill_(float(k))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -480,7 +481,7 @@ def main():
         if k >= 2:
             ex_ms.append(e0.elapsed_time(e1))
     assert np.array_equal(out_pass.cpu().numpy().astype(np.int64), passes)
-    ex_s = float(np.mean(ex_ms)) * 1e-3
+    ex_s = float(np.mean(ex_ms)) * 1e-3 if ex_ms else float("nan")
     # kernel alone (no barrier), and one instrumented launch outside every timed region: the distance
     # evaluations actually executed
     k_ms = []
@@ -504,30 +505,36 @@ def main():
     e2e = None
     if not args.no_e2e:
         eng2 = gicp.IcpEngine(local)
-        if world > 1:
-            eng2.set_tuning("pack_threads", max(1, min(8, len(os.sched_getaffinity(0)) // 1)))
+        # host threads that pack the list into pinned staging: this rank's share of the host's cores
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        eng2.set_tuning("pack_threads", max(1, min(8, len(_ALL_CPUS or os.sched_getaffinity(0)) // max(local_world, 1))))
         rec_pin = torch.empty((n_global, 8), dtype=torch.float64).pin_memory() if gather is not None else None
+        tab_pin = gicp.ScanTable(xy=torch.from_numpy(table.xy).pin_memory().numpy(), offsets=table.offsets)
 
-        def step_host():
-            # scans (list of pageable arrays) + pairs + initial guesses in host memory -> constraints
-            # of ALL ranks in host memory
-            res = eng2.align(scans, pairs_mine, init_mine, epsilon=EPS, max_iters=MAX_ITERS, epilogue=ep)
+        def step_host(scan_arg):
+            # scans + pairs + initial guesses in host memory -> constraints of ALL ranks in host memory
+            res = eng2.align(scan_arg, pairs_mine, init_mine, epsilon=EPS, max_iters=MAX_ITERS, epilogue=ep)
             if gather is not None:
                 gather.barrier()
                 rec_pin.copy_(gather.records(), non_blocking=True)
                 torch.cuda.synchronize()
             return res
 
-        for _ in range(max(min(args.warmup, 5), 2)):
-            res = step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = step_host()
-        barrier()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        def time_host(scan_arg):
+            for _ in range(max(min(args.warmup, 5), 2)):
+                res = step_host(scan_arg)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res = step_host(scan_arg)
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t, res
+
+        t_pin, res = time_host(tab_pin)                       # a pre-packed table in pinned memory, for comparison
+        t_e2e, res = time_host(scans)                         # the reference's own input form: the e2e number
         h2d = table.xy.nbytes + table.offsets.nbytes + pairs_mine.nbytes + (0 if init_mine is None else B * 48) + 4 * B
         d2h = B * (6 * 8 + 8 + 4) + 4 + (0 if gather is None else n_global * 64)
         e2e = {"value": (n_global if args.strong else world * B) * args.steps / float(t_e2e.item()), "unit": UNIT,
@@ -537,7 +544,11 @@ def main():
                         "float64 arrays, packed into pinned staging by the library's host threads while earlier "
                         "pieces are on the wire",
                "call": "IcpEngine.align -> icpb_align_host_scans" + ("" if gather is None else
-                       " with the fused-gather epilogue, symmetric-memory barrier, D2H of all ranks' records")}
+                       " with the fused-gather epilogue, symmetric-memory barrier, D2H of all ranks' records"),
+               "pinned_table": {"value": (n_global if args.strong else world * B) * args.steps / float(t_pin.item()),
+                                "ms_per_step": float(t_pin.item()) / args.steps * 1e3,
+                                "input": "the same scans pre-packed as one (sum m_i, 2) table in pinned memory "
+                                         "(icpb_align_host_ex): no host packing, one read of host memory per byte"}}
         assert np.array_equal(res.iters, passes.astype(np.int32))
         eng2.close()
 
