@@ -310,7 +310,7 @@ struct icpb_ctx {
     PinnedBuf stage_xy;                             // pinned copy of a scan table packed from a list of arrays
     PackPool *pool = nullptr;                       // host threads that pack scans into stage_xy
     // tuning / test hooks (icpb_set_tuning); 0 or -1 = the library's own choice
-    int tune_threads = 0, tune_cluster = -1, tune_segments = 0, tune_sgd_cluster = 0, tune_pack_threads = 0;
+    int tune_threads = 0, tune_cluster = -1, tune_segments = 0, tune_pack_threads = 0;
     bool tune_flag_copy = false, tune_drop_counter = false, tune_trace = false, tune_prepack = false;
 };
 
@@ -547,7 +547,6 @@ int icpb_set_tuning(icpb_handle h, const char *key, int64_t value)
     if (!strcmp(key, "threads")) h->tune_threads = v;
     else if (!strcmp(key, "cluster")) h->tune_cluster = v;
     else if (!strcmp(key, "segments")) h->tune_segments = v;
-    else if (!strcmp(key, "sgd_cluster")) h->tune_sgd_cluster = v;
     else if (!strcmp(key, "pack_threads")) {
         if (h->pool && (int)h->pool->workers.size() != v - 1) { delete h->pool; h->pool = nullptr; }
         h->tune_pack_threads = v;
@@ -1345,46 +1344,27 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
     if (ve.empty() || n_steps == 0) return 0;
     ON_DEVICE(h);
     const size_t E = ve.size() / 2, N = (size_t)n;
-    // [poses 3N | tf 6E | dW 4E | PB 6E | M 3N | P 3N] doubles, then [edges 2E] int32
-    const size_t n_dbl = 3 * N + 6 * E + 4 * E + 6 * E + 3 * N + 3 * N;
+    // [poses 3N | tf 6E | dW 4E | PB 10E | REC 10E | ES 23E | M 3N | P 3N] doubles, then [edges 2E] int32
+    const size_t n_dbl = 3 * N + 6 * E + 4 * E + 10 * E + 10 * E + 23 * E + 3 * N + 3 * N;
     int rc;
     if ((rc = h->s_sgd.reserve(sizeof(double) * n_dbl + sizeof(int32_t) * 2 * E))) return rc;
     double *d_poses = (double *)h->s_sgd.p, *d_tf = d_poses + 3 * N, *d_dW = d_tf + 6 * E, *d_PB = d_dW + 4 * E;
-    double *d_M = d_PB + 6 * E, *d_P = d_M + 3 * N;
+    double *d_REC = d_PB + 10 * E, *d_ES = d_REC + 10 * E, *d_M = d_ES + 23 * E, *d_P = d_M + 3 * N;
     int32_t *d_edges = (int32_t *)(d_P + 3 * N);
     CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_tf, vt.data(), sizeof(double) * 6 * E, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_edges, ve.data(), sizeof(int32_t) * 2 * E, cudaMemcpyHostToDevice, h->stream));
     icpb::SgdArgs a;
     a.poses = d_poses; a.edges = d_edges; a.tf = d_tf; a.n = (int32_t)n; a.E = (int32_t)E;
-    a.lcu = loop_closure_uncertainty; a.dW = d_dW; a.PB = d_PB; a.M = d_M; a.P = d_P;
-    // poses in shared memory: one CTA up to 9,600 nodes, a thread-block cluster of up to 8 CTAs
-    // (one slice of nodes each, distributed shared memory) up to 76,800, global memory beyond that
-    const size_t smem_cap = (size_t)kMaxSmem - 1024;                              // ~0.7 KB of static shared memory
-    const size_t node_cap = smem_cap / (3 * sizeof(double));
-    const size_t scan_bytes = sizeof(double) * 3 * icpb::kSgdThreads;
-    int csize = (int)((N + node_cap - 1) / node_cap);
-    if (h->tune_sgd_cluster >= 1 && h->tune_sgd_cluster <= 8 && (size_t)h->tune_sgd_cluster * node_cap >= N)
-        csize = h->tune_sgd_cluster;                             // icpb_set_tuning("sgd_cluster"), tests
-    a.poses_in_smem = csize <= 8 ? 1 : 0;
-    if (!a.poses_in_smem) csize = 1;
-    a.slice = (int32_t)((N + csize - 1) / csize);
-    size_t dyn = a.poses_in_smem ? sizeof(double) * 3 * (size_t)a.slice : 0;
-    if (dyn < scan_bytes) dyn = scan_bytes;
-    void (*chain)(const icpb::SgdArgs) = csize > 1 ? icpb::sgd_chain_kernel<true> : icpb::sgd_chain_kernel<false>;
-    CU(cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    a.lcu = loop_closure_uncertainty; a.dW = d_dW; a.PB = d_PB; a.REC = d_REC; a.ES = d_ES; a.M = d_M; a.P = d_P;
+    // per pass: weights of the edges, their sum per node, the lazy chain over the edges on one SM (the
+    // only sequential part), then every record applied to every node on all SMs
     for (int32_t k = 0; k < n_steps; ++k) {
         a.learning_rate = h_learning_rates[k];
         icpb::sgd_weights_kernel<<<(unsigned)((E + 255) / 256), 256, 0, h->stream>>>(a);
         icpb::sgd_accumulate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(a);
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned)csize); lc.blockDim = dim3(icpb::kSgdThreads);
-        lc.dynamicSmemBytes = dyn; lc.stream = h->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        lc.attrs = attr; lc.numAttrs = csize > 1 ? 1 : 0;
-        CU(cudaLaunchKernelEx(&lc, chain, a));
+        icpb::sgd_chain_kernel<<<1, icpb::kSgdThreads, 0, h->stream>>>(a);
+        icpb::sgd_apply_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(a);
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(h_poses, d_poses, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, h->stream));

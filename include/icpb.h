@@ -255,7 +255,9 @@ int icpb_compose_chain(const double *pose0, const double *T6, int64_t n, double 
  *              exactly as the reference ignores them (:14-16), edges with b <= a move nothing
  *   h_edge_T6  n_edges x 6 float64: the top two rows of every edge's 3x3 transform (bottom row
  *              [0 0 1], as add_constraint receives it from the ICP path, src/pose_graph.py:38-40)
- * Results agree with the reference to rounding (closed-form 3x3 inverses, prefix sums).
+ * Results agree with the reference to rounding (closed-form 3x3 inverses, prefix sums; the goldens
+ * of the unmodified reference are met to 1e-12).  Any number of poses: the sequential part of a pass
+ * works on 80-byte per-edge records, not on the poses (csrc/icpb_sgd.cuh).
  */
 int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t *h_edges,
                         const double *h_edge_T6, int64_t n_edges, const double *h_learning_rates,
@@ -293,7 +295,7 @@ int icpb_get_kernel_info(icpb_handle h, int64_t B, icpb_kernel_info *out);
 /* Tuning and test hooks, per handle (nothing is read from the environment).  Keys: "threads" (CTA
  * width cap, multiple of 32), "cluster" (force a cluster size: 0/1 never, 2/4/8), "segments" (upload
  * pieces), "pack_threads" (host threads of icpb_align_host_scans, default min(8, cpus)),
- * "sgd_cluster", "flag_copy" (arrival counter by 4-byte copies), "drop_counter" (tests: never
+ * "flag_copy" (arrival counter by 4-byte copies), "drop_counter" (tests: never
  * advance the arrival counter), "trace" (host timings on stderr).  0 / -1 restore the default. */
 int icpb_set_tuning(icpb_handle h, const char *key, int64_t value);
 
