@@ -71,6 +71,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     ap.add_argument("--no-sustained", action="store_true", help="skip the sustained-clock segment")
     ap.add_argument("--no-exhaustive", action="store_true", help="skip the pruning-off launches (long workloads)")
+    ap.add_argument("--threads", type=int, default=0, help="tuning: cap on the CTA width (icpb_set_tuning)")
     args = ap.parse_args()
     dflt = {"chain": (5000, 1024), "proximity": (5000, 1024), "allpairs": (600, 1024), "highres": (48, 4096)}
     args.scans = args.scans or dflt[args.workload][0]
@@ -348,6 +349,8 @@ def main():
     pairs_mine = np.ascontiguousarray(pairs[mine])
     init_mine = None if init is None else np.ascontiguousarray(init[mine])
     eng = gicp.IcpEngine(local)
+    if args.threads:
+        eng.set_tuning("threads", args.threads)
     table = gicp.ScanTable(scans)
     lens = table.lengths
     xy_t, off_t = torch.from_numpy(table.xy).to(dev), torch.from_numpy(table.offsets).to(dev)

@@ -72,7 +72,7 @@ struct DeviceGuard {
 #endif
 constexpr int kPointsPerThread = ICPB_R;
 constexpr int kQueueRing = 64;
-constexpr int kMaxSmem = 227 * 1024;
+
 
 struct DevBuf {
     void *p = nullptr;
@@ -321,15 +321,24 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
     if (longest <= 0) return fail(ICPB_EINVAL, "empty scan table%s");
     const int64_t ntile = (longest + 63) / 64;              // 64-point reduction tiles (independent of R)
     const int64_t nwork = (ntile + R / 2 - 1) / (R / 2);    // warp work items of 32*R points
-    int threads = (int)(nwork * 32);                      // one warp per work item, up to 8 warps
-    // Small CTAs keep more independent problems in flight per SM (less idling at the per-pass
-    // barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
-    // problems per resident CTA (tail) or a single pair (latency).
-    int max_threads = (B >= 2048 && R < 4) ? 128 : 256;
+    // Warps per CTA.  Small CTAs keep more independent problems in flight per SM (less idling at the
+    // per-pass barrier); large CTAs finish a problem sooner, which matters when the batch is only a few
+    // problems per resident CTA (tail) or a single pair (latency).  Within the cap, the count that leaves
+    // the fewest warps idle in the last round of a pass wins (360-beam scans have 6 tiles: 3 warps take
+    // two each, 12.2 M pairs/s, where 4 warps left two idle every second round, 11.5 M), larger on ties.
+    int max_warps = (B >= 2048 && R < 4) ? 4 : 8;
     if (h->tune_threads >= 32 && h->tune_threads <= 256 && h->tune_threads % 32 == 0)
-        max_threads = h->tune_threads;                    // icpb_set_tuning("threads")
-    if (threads > max_threads) threads = max_threads;
-    if (threads < 32) threads = 32;
+        max_warps = h->tune_threads / 32;                 // icpb_set_tuning("threads")
+    int warps = 1;
+    {
+        int64_t best_waste = -1;
+        for (int w = max_warps < nwork ? max_warps : (int)nwork; w >= (max_warps >= 2 && nwork >= 2 ? 2 : 1); --w) {
+            const int64_t waste = (nwork + w - 1) / w * w - nwork;
+            if (best_waste < 0 || waste < best_waste) { best_waste = waste; warps = w; }
+        }
+        if (h->tune_threads > 0) warps = max_warps < nwork ? max_warps : (int)nwork;   // forced: no search
+    }
+    int threads = warps * 32;
     const icpb::SmemLayout L = icpb::smem_layout(longest, threads / 32);
     const int64_t smem = L.bytes;
     if (smem > h->smem_limit) {
@@ -338,13 +347,15 @@ int make_cfg(icpb_ctx *h, int64_t longest, int64_t B, LaunchCfg *c, kernel_fn fn
         return ICPB_ETOOLONG;
     }
     c->threads = threads; c->smem = (int)smem; c->L = L;
-    // Latency mode: with fewer problems than SMs and more than two tiles per warp of a CTA, spread each
-    // problem over a thread-block cluster (a power of two, at most 8 CTAs) so every tile gets a warp.
-    // 1,024-point scans (16 tiles, two per warp) do not qualify: the per-pass cluster barrier and the
-    // fold over distributed shared memory cost more than the second tile (40 pairs: 0.41 ms in single
-    // CTAs, 0.61 ms in clusters of two; tools/midsize_probe.py); 4,096-point pairs gain 1.8x.
+    // Latency mode: when every CTA of every cluster can have an SM of its own and a CTA's eight warps
+    // would each get more than one tile per pass, spread each problem over a thread-block cluster (a
+    // power of two, at most 8 CTAs) so that every tile has a warp.  Measured with one cluster per
+    // problem resident (tools/latency.py, tools/midsize_probe.py, round 2): one 1,024-point pair 0.165 ms
+    // in a CTA, 0.153 in a cluster of two, 0.141 in eight; 40 such pairs 0.37 -> 0.31 ms with clusters of
+    // two, 80 pairs 0.41 -> 0.38; from 120 pairs on (more CTAs than SMs) single CTAs win; one 4,096-point
+    // pair 0.78 -> 0.41 ms in a cluster of eight.
     c->cluster = 1;
-    if (fn == pick_kernel(nullptr) && B * 2 <= h->sm_count && nwork > 16) {
+    if (fn == pick_kernel(nullptr) && nwork > 8) {
         int cl = 2;
         while (cl < 8 && (int64_t)cl * 8 < nwork) cl *= 2;
         while (cl > 1 && B * cl > h->sm_count) cl /= 2;

@@ -10,9 +10,9 @@ for name in "$@"; do
 import json, sys
 f = sys.argv[1]
 try:
-    j = json.load(open(f"gpurun_out/ab_{f}.json")); r = j["roofline"]; k = j["config"]["kernel"]
+    j = json.load(open(f"gpurun_out/ab_{f}.json")); r = j["roofline"]; k = j["details"]["kernel"]
     print(f, round(j["value"]), round(j["ms_per_step"], 3), "exh", round(r.get("exhaustive", {}).get("frac", 0), 3),
-          "share", round(r.get("executed_share"), 4), k["threads_per_cta"], k["ctas_per_sm"], k["regs_per_thread"])
+          "share", round(r["algorithmic"]["executed_share"], 4), k["threads_per_cta"], k["ctas_per_sm"], k["regs_per_thread"])
 except Exception as e:
     print(f, "ERR", e)
 PY
