@@ -22,7 +22,8 @@ EXPORTS = ["icpb_default_params", "icpb_abi_version", "icpb_create", "icpb_destr
            "icpb_proximity_closest", "icpb_proximity_pairs", "icpb_compose_chain",
            "icpb_run_device_gather", "icpb_pose_graph_sgd", "icpb_occupancy_grid_bounds",
            "icpb_occupancy_grid_update", "icpb_run_device_ex", "icpb_align_host_ex", "icpb_align_host_scans",
-           "icpb_set_tuning", "icpb_scan_count"]
+           "icpb_set_tuning", "icpb_scan_count", "icpb_align_host_accept",
+           "icpb_compose_chain_device", "icpb_compose_chain_gpu"]
 
 
 class IcpbParams(ctypes.Structure):
@@ -61,6 +62,7 @@ def sources():
                                               os.path.join(c, "icpb_candidates.cuh"),
                                               os.path.join(c, "icpb_sgd.cuh"),
                                               os.path.join(c, "icpb_grid.cuh"),
+                                              os.path.join(c, "icpb_compose.cuh"),
                                               os.path.join(_ROOT, "include", "icpb.h")]
 
 
@@ -161,6 +163,9 @@ def lib() -> ctypes.CDLL:
     L.icpb_align_host_scans.argtypes = [vp, vp, vp, i64, i32p, dp, ctypes.c_int32, i64, ctypes.POINTER(IcpbParams),
                                         dp, ctypes.c_int32, dp, i32p, ctypes.POINTER(IcpbEpilogue)]
     L.icpb_set_tuning.argtypes = [vp, ctypes.c_char_p, i64]
+    L.icpb_align_host_accept.argtypes = [vp, dp, vp, vp, vp, i64, i32p, dp, ctypes.c_int32, i64,
+                                         ctypes.POINTER(IcpbParams), ctypes.c_double, i64,
+                                         ctypes.POINTER(ctypes.c_int64), vp, dp, ctypes.c_int32, dp, i32p]
     L.icpb_run_host.argtypes = [vp, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p, dp, i32p]
     L.icpb_align_host.argtypes = [vp, dp, vp, i64, i32p, dp, i64, ctypes.POINTER(IcpbParams), dp, dp, i32p]
     L.icpb_align_host_ld.argtypes = [vp, dp, vp, i64, i32p, dp, ctypes.c_int32, i64, ctypes.POINTER(IcpbParams),
@@ -169,6 +174,8 @@ def lib() -> ctypes.CDLL:
     L.icpb_proximity_pairs.argtypes = [vp, dp, dp, i64, ctypes.c_double, ctypes.c_double, i64, i32p,
                                        ctypes.POINTER(ctypes.c_int64)]
     L.icpb_compose_chain.argtypes = [dp, dp, i64, dp]
+    L.icpb_compose_chain_device.argtypes = [vp, dp, dp, i64, dp, vp]
+    L.icpb_compose_chain_gpu.argtypes = [vp, dp, dp, i64, dp]
     L.icpb_pose_graph_sgd.argtypes = [vp, dp, i64, i32p, dp, i64, dp, ctypes.c_int32, ctypes.c_double]
     L.icpb_occupancy_grid_bounds.argtypes = [vp, dp, i64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

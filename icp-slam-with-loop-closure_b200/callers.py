@@ -85,6 +85,18 @@ def compose_chain(pose0, transforms) -> np.ndarray:
     return out
 
 
+def compose_chain_gpu(pose0, transforms, device=None) -> np.ndarray:
+    """`compose_chain` through the device scan (icpb_compose_chain_gpu): same poses to rounding."""
+    T = np.asarray(transforms, dtype=np.float64)
+    T6 = np.ascontiguousarray(T[:, :2, :].reshape(-1, 6))
+    p0 = np.ascontiguousarray(pose0, dtype=np.float64)
+    out = np.empty((len(T6) + 1, 3))
+    e = _icp.engine(device)
+    _icp._lib.check(e._L.icpb_compose_chain_gpu(e._h, _icp._ptr(p0), _icp._ptr(T6), len(T6), _icp._ptr(out)),
+                    "icpb_compose_chain_gpu")
+    return out
+
+
 def _travelled(xy: np.ndarray) -> np.ndarray:
     """The reference's ``dist_traveled`` (src/loop_closure_detection.py:13-14): cumulative sum of the
     consecutive pose distances, first entry 0.  O(S) on the host, in numpy's summation order."""
@@ -140,22 +152,26 @@ def proximity_loop_closures(poses, lidar_points, min_dist_along_path=2, max_dist
     (source = scan j, target = scan i, identity initial guess, :31-34) and the reference's greedy
     loop -- skip a candidate if either endpoint was already used by an *accepted* one, accept if
     error < err_thresh -- is replayed on the results (:27-39).  Returns a list of
-    (i, j, T 3x3) ready for ``pose_graph.add_constraint(i, j, T)``, and the BatchResult."""
+    (i, j, T 3x3) ready for ``pose_graph.add_constraint(i, j, T)``, and the BatchResult of the candidates
+    that passed the threshold."""
     cand = proximity_candidates(poses, min_dist_along_path, max_dist, device)
     if len(cand) == 0:
         return [], None
     pairs = np.stack((cand[:, 1], cand[:, 0]), axis=1).astype(np.int32)
-    res = _icp.icp_batch(lidar_points, pairs, None, epsilon=epsilon, max_iters=max_iters, device=device)
+    # the `error < err_thresh` test runs in the kernel epilogue: only the candidates that pass it come
+    # back (a candidate that fails it never marks its endpoints as used, so the greedy loop over the
+    # passing ones, in the reference's order, accepts exactly what the reference accepts)
+    rows, res = _icp.engine(device).align_accept(lidar_points, pairs, err_thresh, None, epsilon=epsilon,
+                                                 max_iters=max_iters)
     used = set()
     out = []
-    for (i, j), T, e in zip(cand, res.T, res.error):
+    for (i, j), T in zip(cand[rows], res.T):
         i, j = int(i), int(j)
         if i in used or j in used:
             continue
-        if e < err_thresh:
-            out.append((i, j, T))
-            used.add(i)
-            used.add(j)
+        out.append((i, j, T))
+        used.add(i)
+        used.add(j)
     return out, res
 
 
@@ -166,13 +182,14 @@ def image_match_loop_closures(good_matches, lidar_points, image_rate=1, icp_err_
     ``i*image_rate`` (source) onto scan ``j*image_rate`` (target) from the identity -- note the
     argument order is the opposite of ``detect_proximity``'s, a reference quirk kept as is -- and
     keep the pairs with error < icp_err_thresh.  Returns [(i*rate, j*rate, T)] in match order, and
-    the BatchResult.  The ORB/matcher front end that produces ``good_matches`` is out of scope."""
+    the BatchResult of the accepted pairs.  The ORB/matcher front end that produces ``good_matches`` is out of scope."""
     gm = np.asarray(good_matches, dtype=np.int64).reshape(-1, 2)
     if len(gm) == 0:
         return [], None
     pairs = (gm * image_rate).astype(np.int32)               # (source = i*rate, target = j*rate)
-    res = _icp.icp_batch(lidar_points, pairs, None, epsilon=epsilon, max_iters=max_iters, device=device)
-    out = [(int(i), int(j), T) for (i, j), T, e in zip(pairs, res.T, res.error) if e < icp_err_thresh]
+    rows, res = _icp.engine(device).align_accept(lidar_points, pairs, icp_err_thresh, None, epsilon=epsilon,
+                                                 max_iters=max_iters)          # filter on the device
+    out = [(int(pairs[r, 0]), int(pairs[r, 1]), T) for r, T in zip(rows, res.T)]
     return out, res
 
 

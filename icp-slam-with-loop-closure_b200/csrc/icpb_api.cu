@@ -8,6 +8,7 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <algorithm>
 #include <atomic>
 #include <thread>
 #include <mutex>
@@ -23,6 +24,7 @@
 #include "icpb_candidates.cuh"
 #include "icpb_sgd.cuh"
 #include "icpb_grid.cuh"
+#include "icpb_compose.cuh"
 
 namespace {
 
@@ -842,10 +844,21 @@ int host_threads_available()
     return n > 0 ? (int)n : 1;
 }
 
+// icpb_align_host_accept: only the pairs that pass the acceptance test come back to the host
+struct AcceptHost {
+    double thresh;
+    int64_t cap;
+    int64_t *n_out, *rows;
+    double *T;
+    int32_t T_ld;
+    double *err;
+    int32_t *passes;
+};
+
 int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t longest,
                const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
                const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
-               const icpb_epilogue *ep)
+               const icpb_epilogue *ep, const AcceptHost *acc = nullptr)
 {
     const bool trace = h->tune_trace;
     const double t_entry = trace ? now_us() : 0.0;
@@ -882,9 +895,20 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
     // pinned staging, 8-byte members first:  up = [init | pairs | seg | order],  down = [T | err | passes]
     const size_t nbI = sizeof(double) * 6 * (size_t)B, nbE = sizeof(double) * (size_t)B, nb4 = sizeof(int32_t) * (size_t)B;
     const size_t nb_up = nbI + 4 * nb4, nb_down = nbI + nbE + nb4 + sizeof(int32_t);   // + the "upload timed out" word
-    if ((rc = h->stage.reserve(nb_up + nb_down))) return rc;
+    if ((rc = h->stage.reserve(nb_up + nb_down + 32))) return rc;
     if ((rc = h->s_init.reserve(nb_up))) return rc;
     if ((rc = h->s_T.reserve(nb_down))) return rc;
+    icpb_epilogue ep_acc;
+    if (acc) {
+        // acceptance on the device: compact records + their count in device scratch, fetched at the end
+        if ((rc = h->s_hist.reserve(sizeof(double) * 8 * (size_t)acc->cap + 16))) return rc;
+        if (ep) ep_acc = *ep; else memset(&ep_acc, 0, sizeof ep_acc);
+        ep_acc.accept_thresh = acc->thresh; ep_acc.accept_cap = acc->cap;
+        ep_acc.d_accept_count = (int64_t *)h->s_hist.p;
+        ep_acc.d_accept_rec = (double *)h->s_hist.p + 2;
+        ep_acc.d_accept_peer_ptrs = nullptr; ep_acc.d_accept_count_peer_ptrs = nullptr;
+        ep = &ep_acc;
+    }
     // ---- from here on the handle's table is being replaced: a failure leaves it without one ----
     h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
     double *pinit = (double *)h->stage.p;
@@ -1066,7 +1090,13 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
     }
     CUA(cudaEventRecord(h->done_ev[0], cs));
     CUA(cudaStreamWaitEvent(cp, h->done_ev[0], 0));
-    CUA(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+    int64_t *acc_cnt = (int64_t *)(tP + B + 2);               // pinned: [timeout word | pad | accepted count]
+    if (!acc) {
+        CUA(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+    } else {                                                  // the timeout word and the count, not the results
+        CUA(cudaMemcpyAsync(tP + B, d_passes + B, sizeof(int32_t), cudaMemcpyDeviceToHost, cp));
+        CUA(cudaMemcpyAsync(acc_cnt, h->s_hist.p, sizeof(int64_t), cudaMemcpyDeviceToHost, cp));
+    }
     const double t_enq = trace ? now_us() : 0.0;
     CUA(cudaStreamSynchronize(cp));
     if (tP[B] != 0) {
@@ -1075,12 +1105,40 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
         rc = launch(h, d_xy, d_off, n_scans, longest, d_pairs, h_init ? d_init : nullptr, B, p,
                     d_T, d_err, d_passes, nullptr, nullptr, cp, 0, nullptr, nullptr, ep);
         if (rc) return align_abort(h, rc);
-        CUA(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+        if (!acc) CUA(cudaMemcpyAsync(tT, d_T, nb_down, cudaMemcpyDeviceToHost, cp));
+        else      CUA(cudaMemcpyAsync(acc_cnt, h->s_hist.p, sizeof(int64_t), cudaMemcpyDeviceToHost, cp));
         CUA(cudaStreamSynchronize(cp));
     }
     // only now does the handle own the new table
     h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
     const double t_sync = trace ? now_us() : 0.0;
+    if (acc) {
+        // the accepted records only: fetch, order by pair id (the kernel appended them as they finished)
+        const int64_t n = *acc_cnt;
+        *acc->n_out = n < 0 ? -n : n;
+        if (n < 0) return fail(ICPB_EINVAL, "icpb_align_host_accept: more pairs accepted than the capacity given%s");
+        std::vector<double> rec(8 * (size_t)n);
+        if (n > 0) {
+            CU(cudaMemcpyAsync(rec.data(), (double *)h->s_hist.p + 2, sizeof(double) * 8 * (size_t)n,
+                               cudaMemcpyDeviceToHost, cp));
+            CU(cudaStreamSynchronize(cp));
+        }
+        std::vector<int64_t> idx((size_t)n);
+        for (int64_t k = 0; k < n; ++k) idx[(size_t)k] = k;
+        auto tag_of = [&](int64_t k) { int64_t t; memcpy(&t, &rec[8 * (size_t)k + 7], sizeof t); return t; };
+        std::sort(idx.begin(), idx.end(), [&](int64_t x, int64_t y) { return (tag_of(x) >> 16) < (tag_of(y) >> 16); });
+        for (int64_t q = 0; q < n; ++q) {
+            const double *r = &rec[8 * (size_t)idx[(size_t)q]];
+            const int64_t tag = tag_of(idx[(size_t)q]);
+            acc->rows[q] = tag >> 16;
+            acc->passes[q] = (int32_t)(tag & 0xffff);
+            acc->err[q] = r[6];
+            double *m = acc->T + (size_t)acc->T_ld * q;
+            memcpy(m, r, 6 * sizeof(double));
+            if (acc->T_ld == 9) { m[6] = 0.0; m[7] = 0.0; m[8] = 1.0; }
+        }
+        return 0;
+    }
     if (T_ld == 6) {
         memcpy(h_T, tT, nbI);
     } else {
@@ -1163,6 +1221,45 @@ int icpb_align_host_scans(icpb_handle h, const double *const *scan_xy, const int
     TableSrc src;
     src.scan_xy = scan_xy; src.offsets = offsets.data();
     return align_impl(h, src, n_scans, longest, h_pairs, h_init, init_ld, B, p, h_T, T_ld, h_err, h_passes, ep);
+}
+
+int icpb_align_host_accept(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
+                           const double *const *scan_xy, const int64_t *scan_len, int64_t n_scans,
+                           const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                           const icpb_params *p, double accept_thresh, int64_t capacity, int64_t *n_accepted,
+                           int64_t *h_rows, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes)
+{
+    if (!h || n_scans <= 0 || B <= 0 || !h_pairs) return fail(ICPB_EINVAL, "icpb_align_host_accept: bad argument%s");
+    if (!((h_xy && h_offsets) || (scan_xy && scan_len))) return fail(ICPB_EINVAL, "icpb_align_host_accept: no scans%s");
+    if ((init_ld != 6 && init_ld != 9) || (T_ld != 6 && T_ld != 9))
+        return fail(ICPB_EINVAL, "icpb_align_host_accept: init_ld / T_ld must be 6 or 9%s");
+    if (capacity < 1 || !n_accepted || !h_rows || !h_T || !h_err || !h_passes || isnan(accept_thresh))
+        return fail(ICPB_EINVAL, "icpb_align_host_accept: bad output arguments%s");
+    int rc = check_params(p, B);
+    if (rc) return rc;
+    if (p->pair_mode != 0 || p->hist_cap > 0 || p->corr_stride > 0)
+        return fail(ICPB_EINVAL, "icpb_align_host_accept: explicit pairs, no history/correspondences%s");
+    if (B >= (int64_t(1) << 31)) return fail(ICPB_EINVAL, "icpb_align_host_accept: at most 2^31 - 1 pairs per call%s");
+    AcceptHost acc = {accept_thresh, capacity, n_accepted, h_rows, h_T, T_ld, h_err, h_passes};
+    TableSrc src;
+    std::vector<int64_t> offsets;
+    int64_t longest = 0;
+    if (h_xy) {
+        if ((rc = validate_offsets(h_offsets, n_scans, &longest))) return rc;
+        src.xy = h_xy; src.offsets = h_offsets;
+    } else {
+        offsets.resize((size_t)n_scans + 1);
+        offsets[0] = 0;
+        for (int64_t sc = 0; sc < n_scans; ++sc) {
+            if (!scan_xy[sc] || scan_len[sc] <= 0)
+                return fail(ICPB_EINVAL, "empty scan in the list (the reference's argmin raises on it)%s");
+            offsets[(size_t)sc + 1] = offsets[(size_t)sc] + scan_len[sc];
+            if (scan_len[sc] > longest) longest = scan_len[sc];
+        }
+        src.scan_xy = scan_xy; src.offsets = offsets.data();
+    }
+    return align_impl(h, src, n_scans, longest, h_pairs, h_init, init_ld, B, p, nullptr, T_ld, nullptr, nullptr,
+                      nullptr, &acc);
 }
 
 int icpb_align_host_ld(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans,
@@ -1326,6 +1423,36 @@ int icpb_compose_chain(const double *pose0, const double *T6, int64_t n, double 
         double *q = poses_out + 3 * (i + 1);
         q[0] = x; q[1] = y; q[2] = atan2(m10, m00);
     }
+    return 0;
+}
+
+/* The same prefix product as a parallel scan on the device (csrc/icpb_compose.cuh).  d_T6 may be the
+ * d_T output of icpb_run_device: the transforms then never visit the host. */
+int icpb_compose_chain_device(icpb_handle h, const double *pose0, const double *d_T6, int64_t n,
+                              double *d_poses_out, void *stream)
+{
+    if (!h || !pose0 || (n > 0 && !d_T6) || n < 0 || !d_poses_out)
+        return fail(ICPB_EINVAL, "icpb_compose_chain_device: bad argument%s");
+    ON_DEVICE(h);
+    icpb::compose_chain_kernel<<<1, icpb::kComposeThreads, 0, (cudaStream_t)stream>>>(d_T6, n, pose0[0], pose0[1], pose0[2],
+                                                                                      d_poses_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+/* Host buffers in and out, through the device scan (for the comparison with the host loop). */
+int icpb_compose_chain_gpu(icpb_handle h, const double *pose0, const double *h_T6, int64_t n, double *h_poses_out)
+{
+    if (!h || !pose0 || (n > 0 && !h_T6) || n < 0 || !h_poses_out)
+        return fail(ICPB_EINVAL, "icpb_compose_chain_gpu: bad argument%s");
+    ON_DEVICE(h);
+    int rc;
+    if ((rc = h->s_pair_xy.reserve(sizeof(double) * (6 * (size_t)n + 3 * (size_t)(n + 1))))) return rc;
+    double *d_T = (double *)h->s_pair_xy.p, *d_P = d_T + 6 * n;
+    if (n > 0) CU(cudaMemcpyAsync(d_T, h_T6, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = icpb_compose_chain_device(h, pose0, d_T, n, d_P, h->stream))) return rc;
+    CU(cudaMemcpyAsync(h_poses_out, d_P, sizeof(double) * 3 * (size_t)(n + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

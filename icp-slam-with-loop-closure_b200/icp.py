@@ -339,6 +339,45 @@ class IcpEngine:
         self.table, self._keep = table, None
         return BatchResult(T33, err, passes, None, None)
 
+    def align_accept(self, scans, pairs, accept_thresh, init_transforms=None, epsilon=0.01, max_iters=100,
+                     stopping_thresh=0.0001, rotation_only=False):
+        """`align` for the loop-closure callers: the acceptance test `error < accept_thresh`
+        (src/loop_closure_detection.py:35-39, :155-159) and the compaction run in the kernel epilogue and
+        only the accepted constraints come back.  Returns (rows, BatchResult): `rows` are ascending
+        indices into `pairs`, the BatchResult holds their results."""
+        p = _params(epsilon, max_iters, stopping_thresh, rotation_only)
+        pairs_a = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        B = len(pairs_a)
+        if B == 0:
+            return np.zeros(0, dtype=np.int64), BatchResult(np.zeros((0, 3, 3)), np.zeros(0), np.zeros(0, dtype=np.int32))
+        p.k_block = B
+        init33 = None
+        if init_transforms is not None:
+            init33 = np.ascontiguousarray(init_transforms, dtype=np.float64)
+            if init33.shape != (B, 3, 3):
+                raise ValueError(f"init_transforms has shape {init33.shape}; expected ({B}, 3, 3)")
+        rows = np.empty(B, dtype=np.int64)
+        T33, err, passes = np.empty((B, 3, 3)), np.empty(B), np.empty(B, dtype=np.int32)
+        n = ctypes.c_int64()
+        prev, self.table = (self.table, self._keep), None
+        try:
+            if isinstance(scans, ScanTable):
+                table, xy, off, ptrs, lens, ns = scans, _ptr(scans.xy), _ptr(scans.offsets), None, None, scans.n_scans
+            else:
+                sl = scans if isinstance(scans, ScanList) else ScanList(scans)
+                table, xy, off, ptrs, lens, ns = ScanTable.from_lengths(sl.lens), None, None, _ptr(sl.ptrs), _ptr(sl.lens), sl.n_scans
+            _lib.check(self._L.icpb_align_host_accept(self._h, xy, off, ptrs, lens, ns, _ptr(pairs_a), _ptr(init33), 9, B,
+                                                      ctypes.byref(p), float(accept_thresh), B, ctypes.byref(n),
+                                                      _ptr(rows), _ptr(T33), 9, _ptr(err), _ptr(passes)),
+                       "icpb_align_host_accept")
+        except Exception:
+            if self._L.icpb_scan_count(self._h) > 0:
+                self.table, self._keep = prev
+            raise
+        self.table, self._keep = table, None
+        k = int(n.value)
+        return rows[:k].copy(), BatchResult(T33[:k].copy(), err[:k].copy(), passes[:k].copy())
+
     def _align_call(self, scans, pairs_a, init33, B, p, T33, err, passes, ep):
         if isinstance(scans, ScanTable):
             table = scans

@@ -206,6 +206,19 @@ int icpb_align_host_scans(icpb_handle h, const double *const *scan_xy, const int
                           const icpb_params *p, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes,
                           const icpb_epilogue *ep);
 
+/* Upload + align + acceptance test, for the loop-closure callers: the reference aligns every candidate
+ * and keeps those with `error < err_thresh` (src/loop_closure_detection.py:35-39 with err_thresh 110,
+ * :155-159 with icp_err_thresh 30).  Here the test and the compaction run in the kernel epilogue, and
+ * only the accepted constraints come back: h_rows[q] = index into h_pairs (ascending, i.e. the callers'
+ * own order), h_T / h_err / h_passes row q its result; *n_accepted their number (<= capacity, else
+ * ICPB_EINVAL with the true count stored).  Scans either packed (h_xy, h_offsets) or as a list
+ * (scan_xy, scan_len); the other pair of pointers NULL. */
+int icpb_align_host_accept(icpb_handle h, const double *h_xy, const int64_t *h_offsets,
+                           const double *const *scan_xy, const int64_t *scan_len, int64_t n_scans,
+                           const int32_t *h_pairs, const double *h_init, int32_t init_ld, int64_t B,
+                           const icpb_params *p, double accept_thresh, int64_t capacity, int64_t *n_accepted,
+                           int64_t *h_rows, double *h_T, int32_t T_ld, double *h_err, int32_t *h_passes);
+
 /* One pair given directly as two (n, 2) float64 host arrays: the reference's
  * icp(pc1, pc2, init_transform, epsilon, max_iters, stopping_thresh, rotation_only)
  * (src/icp.py:72) and, with epsilon = +inf (one pass), icp_iteration() (src/icp.py:55-69). */
@@ -243,6 +256,16 @@ int icpb_proximity_pairs(icpb_handle h, const double *h_xy, const double *h_trav
  * n + 1 rows (x, y, theta); row 0 is pose0, row i + 1 = mat_to_pose(pose_to_mat(row i) @ T_i).
  * Pure host function (no handle): a serial dependency chain. */
 int icpb_compose_chain(const double *pose0, const double *T6, int64_t n, double *poses_out);
+
+/* The same prefix product as a parallel scan on the device (SE(2) composition is associative; the
+ * result differs from the step-by-step loop by rounding only, ~1e-12 at 5,000 steps).
+ * icpb_compose_chain_device: d_T6 (n x 6) and d_poses_out ((n + 1) x 3) are device arrays -- d_T6 can be
+ * the d_T output of icpb_run_device, so the transforms never visit the host; asynchronous on `stream`.
+ * icpb_compose_chain_gpu: host arrays in and out through the same kernel.  Measured against the host
+ * loop in DESIGN.md; the Python callers use whichever is faster for the chain at hand. */
+int icpb_compose_chain_device(icpb_handle h, const double *pose0, const double *d_T6, int64_t n,
+                              double *d_poses_out, void *stream);
+int icpb_compose_chain_gpu(icpb_handle h, const double *pose0, const double *h_T6, int64_t n, double *h_poses_out);
 
 /*
  * Pose-graph relaxation, the consumer of the path's constraints: n_steps

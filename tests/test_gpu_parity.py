@@ -700,3 +700,25 @@ def test_single_target_fit_is_the_identity_rotation(gicp, c_oracle):
                        return_correspondences=True)
     b = gicp.engine().run(np.array([[0, 1]], dtype=np.int32), None, return_history=True, exhaustive=True)
     np.testing.assert_array_equal(a.history, b.history)
+
+
+def test_align_accept_equals_the_host_filter(gicp):
+    """icpb_align_host_accept (upload + align + `error < thresh` + compaction on the device, only the
+    accepted constraints downloaded) against align() followed by the host filter -- packed table and
+    list of arrays, several thresholds, capacity overflow reported."""
+    from icp_slam_b200 import synth
+    rng = np.random.default_rng(3)
+    poses = synth.loop_trajectory(160, step=0.2)
+    scans = synth.scans_from_poses(poses, 360, rng, drop_frac=0.03)
+    pairs = np.stack((rng.integers(0, 160, 700), rng.integers(0, 160, 700)), axis=1).astype(np.int32)
+    e = gicp.IcpEngine()
+    full = e.align(scans, pairs, None, epsilon=0.05, max_iters=60)
+    for thr in (np.percentile(full.error, 20), np.percentile(full.error, 80), -1.0, 1e300):
+        want = np.nonzero(full.error < thr)[0]
+        for form in (scans, gicp.ScanTable(scans)):
+            rows, res = e.align_accept(form, pairs, thr, None, epsilon=0.05, max_iters=60)
+            np.testing.assert_array_equal(rows, want)
+            np.testing.assert_array_equal(res.T, full.T[want])
+            np.testing.assert_array_equal(res.error, full.error[want])
+            np.testing.assert_array_equal(res.iters, full.iters[want])
+    e.close()

@@ -55,10 +55,18 @@ def test_image_match_call_site():
     xy, off = c_oracle.pack(scans)
     pairs = np.array([(i * rate, j * rate) for i, j in good], dtype=np.int32)
     T, err, passes = c_oracle.icp_batch(xy, off, pairs, None, epsilon=0.05, max_iters=100)
-    np.testing.assert_array_equal(res.iters, passes)
-    np.testing.assert_allclose(res.T, T, atol=1e-9)
+    ok = err < 30                                            # the filter runs on the device: accepted pairs only
+    np.testing.assert_array_equal(res.iters, passes[ok])
+    np.testing.assert_allclose(res.T, T[ok], atol=1e-9)
+    np.testing.assert_allclose(res.error, err[ok], rtol=1e-9)
     keep = [(int(p[0]), int(p[1])) for p, e in zip(pairs, err) if e < 30]
     assert [(a, b) for a, b, _ in out] == keep and (21, 21) in keep
+    # a threshold nothing passes, and one everything passes
+    none, r0 = callers.image_match_loop_closures(good, scans, image_rate=rate, icp_err_thresh=0.0)
+    assert none == [] and len(r0) == 0
+    every, r1 = callers.image_match_loop_closures(good, scans, image_rate=rate, icp_err_thresh=1e300)
+    assert len(every) == len(good)
+    np.testing.assert_allclose(r1.T, T, atol=1e-9)
 
 
 def test_candidate_generation_on_gpu():
@@ -167,3 +175,20 @@ def test_strided_scan_matching_loop():
     np.testing.assert_allclose(got, np.array(corrected), rtol=0, atol=1e-12)
     with pytest.raises(ValueError):
         callers.odometry_chain_strided(scans, odo, 3, 5)
+
+
+def test_chain_composition_on_the_device():
+    """the SE(2) prefix product as a parallel scan on the GPU against the reference's
+    step-by-step loop (scripts/main.py:249-256): equal to rounding (1e-9 here; the trajectory contract is
+    1e-4 m), for chains shorter and longer than the scan's 512 runs."""
+    from icp_slam_b200 import callers, synth
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 7, 511, 512, 513, 4999, 20000):
+        T = np.stack([synth.pose_to_mat(p) for p in rng.normal(0, [0.05, 0.05, 0.02], size=(n, 3))]) if n else np.zeros((0, 3, 3))
+        pose0 = np.array([1.5, -2.0, 0.3])
+        want = callers.compose_chain(pose0, T)
+        got = callers.compose_chain_gpu(pose0, T)
+        assert got.shape == (n + 1, 3)
+        np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=0, atol=1e-9)
+        d = np.abs(got[:, 2] - want[:, 2])
+        assert np.all(np.minimum(d, 2 * np.pi - d) < 1e-9)
