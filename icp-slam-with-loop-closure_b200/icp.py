@@ -356,6 +356,12 @@ class IcpEngine:
             init33 = np.ascontiguousarray(init_transforms, dtype=np.float64)
             if init33.shape != (B, 3, 3):
                 raise ValueError(f"init_transforms has shape {init33.shape}; expected ({B}, 3, 3)")
+        if isinstance(scans, ScanTable) and self.table is scans:
+            # the table is already resident: nothing to upload, so nothing to overlap with -- align on it
+            # and filter the (B x 60 byte) results on the host
+            res = self.run(pairs_a, init_transforms, epsilon, max_iters, stopping_thresh, rotation_only)
+            keep = np.nonzero(res.error < accept_thresh)[0]
+            return keep, BatchResult(res.T[keep], res.error[keep], res.iters[keep])
         rows = np.empty(B, dtype=np.int64)
         T33, err, passes = np.empty((B, 3, 3)), np.empty(B), np.empty(B, dtype=np.int32)
         n = ctypes.c_int64()

@@ -69,7 +69,7 @@ def main():
     odo0 = odo - odo[0]
     table = gicp.ScanTable(scans)
     gicp.icp_batch(scans[:4], np.array([[1, 0]], dtype=np.int32))          # CUDA context, first-use costs
-    stages = {}
+    stages, runs = {}, {}
 
     def timed(name, fn):
         t = time.perf_counter()
@@ -77,18 +77,21 @@ def main():
         stages[name] = (time.perf_counter() - t) * 1e3
         return out
 
-    corrected, res = timed("scan_matching", lambda: callers.odometry_chain(table, odo0, max_iters=100, epsilon=0.05))
-    pg = PoseGraph(corrected.copy())
-    loops = timed("loop_closure", lambda: lcd.detect_proximity(pg, table))
-    timed("optimisation", lambda: pgo.optimise(pg, args.sgd_steps))
-    optimised = pg.poses.copy()
-    timed("orientation", lambda: pgo.recompute_pose_graph_orientation(pg, table, 100, 0.05, icp_recompute=True))
-    grid, origin = timed("occupancy_grid", lambda: pog.produce_occupancy_grid(pg.poses, table, args.cell))
+    for attempt in ("first_run_ms", "steady_ms"):                # the second run has every kernel loaded and every buffer sized
+        stages = {}
+        corrected, res = timed("scan_matching", lambda: callers.odometry_chain(table, odo0, max_iters=100, epsilon=0.05))
+        pg = PoseGraph(corrected.copy())
+        loops = timed("loop_closure", lambda: lcd.detect_proximity(pg, table))
+        timed("optimisation", lambda: pgo.optimise(pg, args.sgd_steps))
+        optimised = pg.poses.copy()
+        timed("orientation", lambda: pgo.recompute_pose_graph_orientation(pg, table, 100, 0.05, icp_recompute=True))
+        grid, origin = timed("occupancy_grid", lambda: pog.produce_occupancy_grid(pg.poses, table, args.cell))
+        runs[attempt] = {k: round(v, 2) for k, v in stages.items()}
     print(json.dumps({
         "scans": args.scans, "beams_per_scan": args.beams, "chain_pairs": len(pairs),
         "mean_chain_passes": float(res.iters.mean()), "loop_closures": len(loops), "sgd_steps": args.sgd_steps,
-        "grid": list(grid.shape), "stage_ms": {k: round(v, 2) for k, v in stages.items()},
-        "total_ms": round(sum(stages.values()), 2),
+        "grid": list(grid.shape), "stage_ms": runs["steady_ms"], "total_ms": round(sum(runs["steady_ms"].values()), 2),
+        "first_run_stage_ms": runs["first_run_ms"],
         "ate_m": {"scan_matching": ate(corrected, truth0), "optimised": ate(optimised, truth0)},
     }))
 
