@@ -583,7 +583,7 @@ def main():
                           "timed kernel EXECUTED (counted by an instrumented launch of the same kernel) / its "
                           "average duration; frac = the share of the FP32 pipe's lane-slots it used",
             "kernel_ms": kern_s * 1e3, "executed_pde_per_launch": executed,
-            "algorithmic": {"pde_per_launch": work, "executed_share": executed / work,
+            "algorithmic": {"pde_per_launch": work, "executed_share": executed / max(work, 1.0),
                             "speedup_over_exhaustive_sweep": ex_s / kern_s,
                             "note": "passes*N1*N2 is what the reference's brute force evaluates; exact chunk pruning "
                                     "proves the rest unnecessary (bit-identical results, tests/test_gpu_parity.py)"},
