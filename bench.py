@@ -590,8 +590,8 @@ def main():
             "exhaustive": {"kernel_ms": ex_s * 1e3, "achieved": work / ex_s * 1e-12, "frac": work / ex_s / pde_peak,
                            "pairs_per_s": B / ex_s,
                            "note": "the same kernel with pruning off: every distance executed, the variant the "
-                                   "FP32-pipe roofline bounds; with the min tree on the ALU pipe (which does not "
-                                   "overlap with packed f32x2 instructions, profiles/r02_micro_pipes.log) the "
+                                   "FP32-pipe roofline bounds; with the min tree on the ALU pipe (which all but "
+                                   "serialises with packed f32x2 instructions, profiles/r02_micro_pipes.log) the "
                                    "attainable fraction is 0.80"},
             "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kern_s * 1e-9,
                          "peak_gbs": hbm_peak, "frac": alg_bytes / kern_s * 1e-9 / hbm_peak, "peak_source": peak_src},
