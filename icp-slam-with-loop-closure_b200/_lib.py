@@ -79,8 +79,15 @@ def build_pyhelper(force: bool = False) -> str:
     with open(os.path.join(_HERE, ".build.lock"), "w") as lk:
         fcntl.flock(lk, fcntl.LOCK_EX)
         tmp = f"{PYHELPER_SO}.{os.getpid()}.tmp"
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"],
-                               "-o", tmp, PYHELPER_SRC])
+        cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"]]
+        try:                                                # numpy's C API when its headers are there
+            import numpy
+            inc = numpy.get_include()
+            if os.path.exists(os.path.join(inc, "numpy", "arrayobject.h")):
+                cmd += ["-DICPB_WITH_NUMPY", "-I", inc]
+        except ImportError:
+            pass
+        subprocess.check_call(cmd + ["-o", tmp, PYHELPER_SRC])
         os.replace(tmp, PYHELPER_SO)
     return PYHELPER_SO
 

@@ -864,25 +864,6 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
     const double t_entry = trace ? now_us() : 0.0;
     const int64_t *h_offsets = src.offsets;
     int rc;
-    {
-        int32_t lo = 0, hi = 0;                               // branch-free range check
-        for (int64_t b = 0; b < 2 * B; ++b) { lo = h_pairs[b] < lo ? h_pairs[b] : lo; hi = h_pairs[b] > hi ? h_pairs[b] : hi; }
-        if (lo < 0 || hi >= n_scans) return fail(ICPB_EINVAL, "pair index out of range%s");
-    }
-    if (h_init && B > 0) {                                    // before any state of the handle changes
-        for (int64_t b = 0; b < B && init_ld == 9; ++b) {
-            const double *m = h_init + 9 * b;
-            if (!(m[6] == 0.0 && m[7] == 0.0 && m[8] == 1.0))
-                return fail(ICPB_EINVAL, "transform bottom row must be [0, 0, 1] (an SE(2) matrix)%s");
-        }
-        uint64_t bad = 0;                                     // all-ones exponent = inf or NaN; integer test, vectorises
-        for (int64_t k = 0; k < (int64_t)init_ld * B; ++k) {
-            uint64_t u;
-            memcpy(&u, h_init + k, sizeof u);
-            bad |= (uint64_t)((u & 0x7ff0000000000000ULL) == 0x7ff0000000000000ULL);
-        }
-        if (bad) return fail(ICPB_EINVAL, "transform holds non-finite values%s");
-    }
     ON_DEVICE(h);
     const size_t nb_xy = sizeof(double) * 2 * (size_t)h_offsets[n_scans];
     const size_t nb_off = sizeof(int64_t) * (size_t)(n_scans + 1);
@@ -909,8 +890,6 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
         ep_acc.d_accept_peer_ptrs = nullptr; ep_acc.d_accept_count_peer_ptrs = nullptr;
         ep = &ep_acc;
     }
-    // ---- from here on the handle's table is being replaced: a failure leaves it without one ----
-    h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
     double *pinit = (double *)h->stage.p;
     int32_t *ppairs = (int32_t *)(pinit + 6 * B), *pseg = ppairs + 2 * B, *porder = pseg + B;
     double *tT = (double *)((char *)h->stage.p + nb_up), *tE = tT + 6 * B;
@@ -968,6 +947,30 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
         }                                                                                 \
     } while (0)
 
+    // The packers (list input) are already at work on the pinned staging; the caller's pairs and initial
+    // guesses are checked now, before any state of the handle changes: a rejected call leaves the old
+    // table usable.
+    {
+        int32_t lo = 0, hi = 0;                               // branch-free range check
+        for (int64_t b = 0; b < 2 * B; ++b) { lo = h_pairs[b] < lo ? h_pairs[b] : lo; hi = h_pairs[b] > hi ? h_pairs[b] : hi; }
+        if (lo < 0 || hi >= n_scans) { pack_finish(); return fail(ICPB_EINVAL, "pair index out of range%s"); }
+    }
+    if (h_init && B > 0) {                                    // before any state of the handle changes
+        for (int64_t b = 0; b < B && init_ld == 9; ++b) {
+            const double *m = h_init + 9 * b;
+            if (!(m[6] == 0.0 && m[7] == 0.0 && m[8] == 1.0))
+            { pack_finish(); return fail(ICPB_EINVAL, "transform bottom row must be [0, 0, 1] (an SE(2) matrix)%s"); }
+        }
+        uint64_t bad = 0;                                     // all-ones exponent = inf or NaN; integer test, vectorises
+        for (int64_t k = 0; k < (int64_t)init_ld * B; ++k) {
+            uint64_t u;
+            memcpy(&u, h_init + k, sizeof u);
+            bad |= (uint64_t)((u & 0x7ff0000000000000ULL) == 0x7ff0000000000000ULL);
+        }
+        if (bad) { pack_finish(); return fail(ICPB_EINVAL, "transform holds non-finite values%s"); }
+    }
+    // ---- from here on the handle's table is being replaced: a failure leaves it without one ----
+    h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
     cudaStream_t cp = h->stream, cp2 = h->cstream[1], cs = h->cstream[0];
     if (B == 0) {                                             // upload only
         if (src.scan_xy) { pack_run(&job); pack_finish(); }

@@ -456,7 +456,10 @@ template <int R, bool PRUNE, bool CLUSTER>
 #ifndef ICPB_MIN_CTAS
 #define ICPB_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, (CLUSTER ? 1 : (R >= 4 ? 2 : ICPB_MIN_CTAS)))
+#ifndef ICPB_EXH_CTAS
+#define ICPB_EXH_CTAS 2
+#endif
+__global__ void __launch_bounds__(256, (CLUSTER ? 1 : (R >= 4 ? ICPB_EXH_CTAS : ICPB_MIN_CTAS)))
 icp_align_kernel(const KernelArgs a)
 {
     float  *tqx    = reinterpret_cast<float *>(smem_raw);
