@@ -313,7 +313,7 @@ struct icpb_ctx {
     PackPool *pool = nullptr;                       // host threads that pack scans into stage_xy
     // tuning / test hooks (icpb_set_tuning); 0 or -1 = the library's own choice
     int tune_threads = 0, tune_cluster = -1, tune_segments = 0, tune_pack_threads = 0;
-    bool tune_flag_copy = false, tune_drop_counter = false, tune_trace = false, tune_prepack = false;
+    bool tune_flag_copy = false, tune_drop_counter = false, tune_trace = false;
 };
 
 namespace {
@@ -567,7 +567,6 @@ int icpb_set_tuning(icpb_handle h, const char *key, int64_t value)
     else if (!strcmp(key, "flag_copy")) h->tune_flag_copy = v != 0;
     else if (!strcmp(key, "drop_counter")) h->tune_drop_counter = v != 0;
     else if (!strcmp(key, "trace")) h->tune_trace = v != 0;
-    else if (!strcmp(key, "prepack")) h->tune_prepack = v != 0;
     else return fail(ICPB_EINVAL, "icpb_set_tuning: unknown key %s", key);
     return 0;
 }
@@ -1059,7 +1058,6 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
                 d_T, d_err, d_passes, nullptr, nullptr, cs, B, d_seg, h->arrived_dev, ep,
                 in_order ? nullptr : d_order, d_passes + B);
     if (rc) { pack_finish(); return align_abort(h, rc); }
-    if (src.scan_xy && h->tune_prepack) { pack_run(&job); if (h->pool) h->pool->finish(); }   // experiment: no overlap
     bool bad_scans = false;
     double t_ready[kMaxSegments] = {0}, t_enqd[kMaxSegments] = {0};   // trace: piece k packed / enqueued (host clock)
     cudaEvent_t tev[kMaxSegments + 1] = {nullptr};            // trace: when piece k had landed (device clock)

@@ -13,11 +13,12 @@
 //     all-fp64 search, and fp32 only decides how much fp64 work is needed;
 //   * transform application, centroids, cross-covariance, error, composition and the stop
 //     rules are fp64, reduced in a fixed order (deterministic).
-//   * Exact pruning: 16-target chunks carry a bounding circle; a warp skips a chunk only when the
-//     triangle inequality proves that every target in it is farther from every one of the warp's
-//     128 source points than that point's current upper bound (its filter distance to the
-//     previous pass's match) plus the rounding bound.  Skipped targets can therefore never be a
-//     candidate of the exact decision, so the result is that of the exhaustive search.
+//   * Exact pruning: 16-target chunks carry a bounding circle; a group of lanes (16 source points)
+//     skips a chunk only when the triangle inequality proves that every target in it is farther
+//     from every one of the group's points than that point's current upper bound (its filter
+//     distance to the previous pass's match) plus the rounding bound.  Skipped targets can
+//     therefore never be a candidate of the exact decision, so the result is that of the
+//     exhaustive search.
 #pragma once
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
@@ -353,43 +354,6 @@ __device__ __forceinline__ float group_min(float v)
 #pragma unroll
     for (int o = kLpg / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
-}
-
-// Butterfly reduction of 8 doubles across the warp: each level halves the number of values a lane
-// carries (lanes exchange the half they do not keep), then two plain levels finish.  9 double
-// shuffles instead of 40.  Afterwards lane L holds the warp total of value
-// id = 4*bit4(L) + 2*bit3(L) + bit2(L).  The addition order is fixed, so the result is
-// deterministic.
-__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
-{
-    double w4[4], w2[2], w1;
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double send = up ? v[j] : v[j + 4];
-            const double keep = up ? v[j + 4] : v[j];
-            w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const double send = up ? w4[j] : w4[j + 2];
-            const double keep = up ? w4[j + 2] : w4[j];
-            w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
-        const double send = up ? w2[0] : w2[1];
-        const double keep = up ? w2[1] : w2[0];
-        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-    return w1;
 }
 
 // filter distance minus a threshold, for the decision step's candidate test: the sign bit of

@@ -1,5 +1,9 @@
+#!/usr/bin/env python
+"""Host-to-host time of IcpEngine.align on the headline workload for the three input forms (list of
+pageable arrays, prebuilt ScanList, pinned table), and one traced call: when every upload piece was
+packed, enqueued and had landed (developer probe)."""
 import sys, time, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from icp_slam_b200 import icp as gicp, synth
 scans, pairs, init, _, _ = synth.make_chain_workload(5000, 1024, seed=467002)
