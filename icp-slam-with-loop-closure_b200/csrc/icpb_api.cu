@@ -309,6 +309,10 @@ struct icpb_ctx {
     DevBuf s_sgd;                                   // pose-graph SGD: poses, edges, transforms, scratch
     DevBuf s_grid;                                  // occupancy grid: poses, per-cell words, the grid
     DevBuf s_accept;                                // acceptance epilogue: [appended, CTAs left] counters
+    // per-scan staging images of the resident table (KernelArgs::prep_in), built on first use
+    DevBuf prep;
+    const double *prep_for = nullptr;               // the table (h->xy) the images were built from
+    int64_t prep_stride = 0, prep_scans = 0, prep_longest = 0;
     PinnedBuf stage_xy;                             // pinned copy of a scan table packed from a list of arrays
     PackPool *pool = nullptr;                       // host threads that pack scans into stage_xy
     // tuning / test hooks (icpb_set_tuning); 0 or -1 = the library's own choice
@@ -407,13 +411,17 @@ int check_epilogue(const icpb_epilogue *ep, const icpb_params *p)
     return 0;
 }
 
+int ensure_prep(icpb_ctx *h, cudaStream_t stream);
+
 int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scans, int64_t longest,
            const int32_t *d_pairs, const double *d_init, int64_t B, const icpb_params *p,
            double *d_T, double *d_err, int32_t *d_passes, double *d_hist, int32_t *d_corr,
            cudaStream_t stream, int64_t B_total = 0, const int32_t *d_seg_of_pair = nullptr,
            const int32_t *d_arrived = nullptr, const icpb_epilogue *ep = nullptr,
-           const int32_t *d_order = nullptr, int32_t *d_upload_timeout = nullptr)
+           const int32_t *d_order = nullptr, int32_t *d_upload_timeout = nullptr,
+           unsigned char *prep_out = nullptr, int64_t prep_stride_out = 0)
 {
+    const bool prep_building = prep_out != nullptr;
     if (B == 0) return 0;
     LaunchCfg cfg;
     kernel_fn fn = pick_kernel(p);
@@ -431,6 +439,14 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     a.o_red = cfg.L.o_red; a.o_tw = cfg.L.o_tw; a.o_s0 = cfg.L.o_s0; a.o_scr = cfg.L.o_scr;
     a.executed = h->executed;
     a.seg_of_pair = d_seg_of_pair; a.arrived = d_arrived; a.order = d_order; a.upload_timeout = d_upload_timeout;
+    a.prep_out = nullptr; a.prep_in = nullptr; a.prep_stride = 0;
+    if (d_arrived == nullptr && xy == h->xy && h->xy != nullptr && !prep_building) {
+        // a resident table: stage every pair by copy from the per-scan images (built once per table)
+        int rc2 = ensure_prep(h, stream);
+        if (rc2) return rc2;
+        if (h->prep_for == h->xy) { a.prep_in = (const unsigned char *)h->prep.p; a.prep_stride = h->prep_stride; }
+    }
+    if (prep_out) { a.prep_out = prep_out; a.prep_stride = prep_stride_out; }
     a.peers = nullptr; a.n_peers = 0; a.rec_row0 = 0; a.rec_block = B > 0 ? B : 1; a.rec_stride = 0;
     a.accept_thresh = 0.0; a.accept_rec = nullptr; a.accept_peers = nullptr; a.accept_ctr = nullptr;
     a.accept_count_out = nullptr; a.accept_count_peers = nullptr; a.accept_cap = 0; a.accept_rank = 0;
@@ -474,6 +490,32 @@ int launch(icpb_ctx *h, const double *xy, const int64_t *offsets, int64_t n_scan
     }
     CU(cudaGetLastError());
     h->launches++;
+    return 0;
+}
+
+// The device form of a resident scan table: besides the fp64 points, one staging image per scan (fp32
+// target arrays, chunk circles, group circles, S0, largest coordinate), built by one launch of the
+// alignment kernel in prep mode the first time the table is used.  A pair's staging is then a 10 KB copy
+// instead of ~11,000 warp instructions; scans that take part in many pairs (loop-closure candidates, all
+// pairs) are prepared once instead of once per pair.  Tables whose images would exceed 8 GB are staged
+// per pair as before.
+int ensure_prep(icpb_ctx *h, cudaStream_t stream)
+{
+    if (h->prep_for == h->xy && h->prep_scans == h->n_scans && h->prep_longest == h->longest) return 0;
+    h->prep_for = nullptr;
+    const icpb::SmemLayout L = icpb::smem_layout(h->longest, 4);
+    const int64_t stride = ((int64_t)L.o_mm + 32 + 15) & ~int64_t(15);
+    if (stride * h->n_scans > (int64_t(8) << 30)) return 0;
+    int rc;
+    if ((rc = h->prep.reserve((size_t)(stride * h->n_scans)))) return rc;
+    icpb_params p;
+    icpb_default_params(&p);
+    p.k_block = h->n_scans;
+    rc = launch(h, h->xy, h->offsets, h->n_scans, h->longest, nullptr, nullptr, h->n_scans, &p,
+                nullptr, nullptr, nullptr, nullptr, nullptr, stream, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                (unsigned char *)h->prep.p, stride);
+    if (rc) return rc;
+    h->prep_for = h->xy; h->prep_stride = stride; h->prep_scans = h->n_scans; h->prep_longest = h->longest;
     return 0;
 }
 
@@ -584,7 +626,7 @@ int icpb_destroy(icpb_handle h)
     if (h->arrived_dev) cudaFree(h->arrived_dev);
     if (h->seg_vals_pinned) cudaFreeHost(h->seg_vals_pinned);
     h->s_seg.release(); h->stage.release(); h->s_sgd.release(); h->s_grid.release();
-    h->s_accept.release(); h->stage_xy.release();
+    h->s_accept.release(); h->stage_xy.release(); h->prep.release();
     h->own_xy.release(); h->own_off.release();
     h->s_pairs.release(); h->s_init.release(); h->s_T.release(); h->s_err.release();
     h->s_passes.release(); h->s_hist.release(); h->s_corr.release();
@@ -621,7 +663,7 @@ int icpb_upload_scans(icpb_handle h, const double *h_xy, const int64_t *h_offset
     CU(cudaMemcpyAsync(h->own_xy.p, h_xy, nb_xy, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->xy = (const double *)h->own_xy.p;
+    h->prep_for = nullptr; h->xy = (const double *)h->own_xy.p;
     h->offsets = (const int64_t *)h->own_off.p;
     h->n_scans = n_scans;
     h->longest = longest;
@@ -633,7 +675,7 @@ int icpb_set_scans_device(icpb_handle h, const double *d_xy, const int64_t *d_of
 {
     if (!h || !d_xy || !d_offsets || n_scans <= 0 || longest_scan <= 0)
         return fail(ICPB_EINVAL, "icpb_set_scans_device: bad argument%s");
-    h->xy = d_xy; h->offsets = d_offsets; h->n_scans = n_scans; h->longest = longest_scan;
+    h->prep_for = nullptr; h->xy = d_xy; h->offsets = d_offsets; h->n_scans = n_scans; h->longest = longest_scan;
     return 0;
 }
 
@@ -820,7 +862,7 @@ int align_abort(icpb_ctx *h, int rc)
     cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->cstream[0]); cudaStreamSynchronize(h->cstream[1]);
     cudaGetLastError();
     memcpy(g_err, keep, sizeof keep);
-    h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
+    h->prep_for = nullptr; h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
     return rc;
 }
 #define CUA(call)                                                                         \
@@ -969,7 +1011,7 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
         if (bad) { pack_finish(); return fail(ICPB_EINVAL, "transform holds non-finite values%s"); }
     }
     // ---- from here on the handle's table is being replaced: a failure leaves it without one ----
-    h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
+    h->prep_for = nullptr; h->xy = nullptr; h->offsets = nullptr; h->n_scans = 0; h->longest = 0;
     cudaStream_t cp = h->stream, cp2 = h->cstream[1], cs = h->cstream[0];
     if (B == 0) {                                             // upload only
         if (src.scan_xy) { pack_run(&job); pack_finish(); }
@@ -977,7 +1019,7 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
         CUA(cudaMemcpyAsync(h->own_xy.p, up_xy, nb_xy, cudaMemcpyHostToDevice, cp));
         CUA(cudaMemcpyAsync(h->own_off.p, h_offsets, nb_off, cudaMemcpyHostToDevice, cp));
         CUA(cudaStreamSynchronize(cp));
-        h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
+        h->prep_for = nullptr; h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
         return 0;
     }
     // The first pieces start NOW, before the per-pair staging below: the copy engine works while the
@@ -1111,7 +1153,7 @@ int align_impl(icpb_handle h, const TableSrc &src, int64_t n_scans, int64_t long
         CUA(cudaStreamSynchronize(cp));
     }
     // only now does the handle own the new table
-    h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
+    h->prep_for = nullptr; h->xy = d_xy; h->offsets = d_off; h->n_scans = n_scans; h->longest = longest;
     const double t_sync = trace ? now_us() : 0.0;
     if (acc) {
         // the accepted records only: fetch, order by pair id (the kernel appended them as they finished)

@@ -137,6 +137,14 @@ struct KernelArgs {
     long long *const *accept_count_peers;
     int64_t  accept_cap;
     int32_t  accept_rank;
+    // Per-scan staging images (the device form of a resident scan table, built once by a launch of this
+    // same kernel with prep_out set): record s holds exactly what the staging phase below leaves in shared
+    // memory for scan s -- target SoA, chunk circles, group circles -- plus S0 and the largest target
+    // coordinate.  With prep_in a pair's staging is a copy: target arrays from the target scan's record,
+    // group circles and S0 from the source scan's.
+    unsigned char       *prep_out;   // != nullptr: problem b is scan b (source = target = b); build its record, no ICP
+    const unsigned char *prep_in;
+    int64_t              prep_stride;
 };
 
 // ---- fp32 filter distance: one definition, used by the sweep and by the refine step ----------
@@ -494,7 +502,9 @@ icp_align_kernel(const KernelArgs a)
         }
 
         int32_t sid, did;
-        if (a.p.pair_mode == 1) {
+        if (a.prep_out) {
+            sid = did = (int32_t)pid;
+        } else if (a.p.pair_mode == 1) {
             const int64_t k = a.p.k_first + (pid / a.p.k_block) * a.p.k_stride + (pid % a.p.k_block);
             int32_t i, j;
             decode_pair(k, a.n_scans, i, j);
@@ -519,6 +529,35 @@ icp_align_kernel(const KernelArgs a)
         const double2 g = dst[0];                 // shifts for the one-pass covariance sums
         const double2 s0 = src[0];
 
+        if (a.prep_in) {
+            // ---------------- staging by copy from the per-scan images ----------------
+            const unsigned char *imgT = a.prep_in + (size_t)did * a.prep_stride;
+            const unsigned char *imgS = a.prep_in + (size_t)sid * a.prep_stride;
+            {
+                const float4 *gx = reinterpret_cast<const float4 *>(imgT), *gy = reinterpret_cast<const float4 *>(imgT + a.o_tqy);
+                float4 *sx4 = reinterpret_cast<float4 *>(tqx), *sy4 = reinterpret_cast<float4 *>(tqy);
+                for (int j = tid; j < (n2pad + kChunk) / 4; j += NT) { sx4[j] = gx[j]; sy4[j] = gy[j]; }
+                const float4 *gc = reinterpret_cast<const float4 *>(imgT + a.o_cb);
+                for (int c = tid; c < ((nchunks + 31) & ~31); c += NT) cb[c] = gc[c];
+                if (PRUNE) {
+                    const float4 *gt = reinterpret_cast<const float4 *>(imgS + a.o_tc);
+                    for (int w = tid; w < nwork * kGroups; w += NT) tc[w] = gt[w];
+                }
+                if (tid == 0) {
+                    const double *g0 = reinterpret_cast<const double *>(imgS + a.o_mm);
+                    S0[0] = g0[0]; S0[1] = g0[1];
+                    s_qmax_bits = *reinterpret_cast<const unsigned int *>(imgT + a.o_mm + 16);
+                }
+            }
+            if (lane < 6) {
+                double v = a.init ? a.init[6 * pid + lane] : ((lane == 0 || lane == 4) ? 1.0 : 0.0);
+                if (a.p.rotation_only && (lane == 2 || lane == 5)) v = 0.0;     // src/icp.py:60-61
+                Tmine[lane] = v;
+            }
+            __syncwarp();
+            if (lane == 0) Tmine[6] = stretch_of(Tmine);
+            __syncthreads();
+        } else {
         // ---------------- stage the target in shared memory as fp32 SoA ----------------
         {
             float qm = 0.0f;
@@ -583,7 +622,6 @@ icp_align_kernel(const KernelArgs a)
             }
         }
         __syncthreads();
-        const float qmax = __uint_as_float(s_qmax_bits);
         // ---------------- bounding circle of every 16-target chunk ----------------
         for (int c = tid; c < nchunks; c += NT) {
             const int j0 = c * kChunk, j1 = min(j0 + kChunk, n2);
@@ -611,6 +649,26 @@ icp_align_kernel(const KernelArgs a)
         }
         if (lane == 0) Tmine[6] = stretch_of(Tmine);
         __syncthreads();
+        }
+        const float qmax = __uint_as_float(s_qmax_bits);
+        if (a.prep_out) {
+            // ---------------- prep mode: this scan's staging image goes to HBM, no ICP ----------------
+            unsigned char *img = a.prep_out + (size_t)pid * a.prep_stride;
+            float4 *gx = reinterpret_cast<float4 *>(img), *gy = reinterpret_cast<float4 *>(img + a.o_tqy);
+            const float4 *sx4 = reinterpret_cast<const float4 *>(tqx), *sy4 = reinterpret_cast<const float4 *>(tqy);
+            for (int j = tid; j < (n2pad + kChunk) / 4; j += NT) { gx[j] = sx4[j]; gy[j] = sy4[j]; }
+            float4 *gc = reinterpret_cast<float4 *>(img + a.o_cb);
+            for (int c = tid; c < ((nchunks + 31) & ~31); c += NT) gc[c] = cb[c];
+            float4 *gt = reinterpret_cast<float4 *>(img + a.o_tc);
+            for (int w = tid; w < nwork * kGroups; w += NT) gt[w] = tc[w];
+            if (tid == 0) {
+                double *g0 = reinterpret_cast<double *>(img + a.o_mm);
+                g0[0] = S0[0]; g0[1] = S0[1];
+                *reinterpret_cast<unsigned int *>(img + a.o_mm + 16) = s_qmax_bits;
+            }
+            sync_all();
+            continue;
+        }
 
         int passes = 0, iteration = 0;
         bool have_last = false;

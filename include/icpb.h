@@ -75,8 +75,9 @@ int icpb_destroy(icpb_handle h);
 
 /* Scan table = the reference's `lidar_points` list (src/dataloader.py:110-112), concatenated.
  * icpb_upload_scans copies host arrays into device memory owned by the handle;
- * icpb_set_scans_device borrows device arrays the caller keeps alive.  offsets has
- * n_scans + 1 entries, offsets[0] = 0. */
+ * icpb_set_scans_device borrows device arrays the caller keeps alive (call it again after changing
+ * their contents: the first launch on a resident table derives per-scan staging data from it, once).
+ * offsets has n_scans + 1 entries, offsets[0] = 0. */
 int icpb_upload_scans(icpb_handle h, const double *h_xy, const int64_t *h_offsets, int64_t n_scans);
 int icpb_set_scans_device(icpb_handle h, const double *d_xy, const int64_t *d_offsets,
                           int64_t n_scans, int64_t longest_scan);
