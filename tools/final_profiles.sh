@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 $cmd > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:icp_align_kernel -s 1 -c 1 -f -o gpurun_out/${tag}_align $cmd > gpurun_out/ncu1.log 2>&1
 $cmd > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:icp_align_kernel -s 4 -c 1 -f -o gpurun_out/${tag}_exh $cmd > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:icp_align_kernel -s 4 -c 2 -f -o gpurun_out/${tag}_exh $cmd > gpurun_out/ncu2.log 2>&1
 cmd2="python tools/slam_pipeline.py --sgd-steps 2"
 $cmd2 > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"sgd_chain|proximity_closest" -c 3 -f -o gpurun_out/${tag}_sgd_prox $cmd2 > gpurun_out/ncu3.log 2>&1
