@@ -14,9 +14,9 @@
 //   * sgd_accumulate_kernel: one thread per node adds the diagonals of the edges covering it, in
 //     edge order (the reference's order of additions, so M has the reference's bits given the
 //     same diagonals); the edge list streams through shared memory;
-//   * sgd_chain_kernel: ONE CTA walks the edges lazily: every edge leaves a record, the endpoints
-//     of the next edge are evaluated from the start-of-pass poses and the records so far (see the
-//     kernel's own comment); node i > a receives beta_j/total_j * (P_j[min(i,b)] - P_j[a]) -- the
+//   * sgd_chain_kernel: ONE CTA walks the edges lazily: every edge leaves a record, and only the
+//     endpoints of the edges still to come are kept up to date (see the kernel's own comment);
+//     node i > a receives beta_j/total_j * (P_j[min(i,b)] - P_j[a]) -- the
 //     reference's running sum `dpose` in closed form over the prefix sums P_j[i] = sum_{k<=i} 1/M[k,j];
 //   * sgd_apply_kernel: one thread per node applies all records, in edge order.
 // All arithmetic is fp64; the results agree with the reference to rounding (the 3x3 inverses are
@@ -38,9 +38,9 @@ struct SgdArgs {
     double        *dW;        // E x 4 scratch: diag(W) and its squared norm (+inf: edge adds no weight)
     double        *M;         // n x 3 scratch: weights
     double        *P;         // n x 3 scratch: inclusive prefix sums of 1/M
-    double        *PB;        // E x 10 scratch: per edge P_j[a], P_j[b] - P_j[a], its reciprocal, atan2(tf[1,0], tf[0,0])
     double        *REC;       // E x 10 scratch: the per-edge records of the lazy chain (SgdRecords)
     double        *ES;        // E x 23 scratch: the per-edge inputs of the chain (SgdEdgeFull)
+    double        *SL;        // E x 13 scratch: the chain's slots when they do not fit shared memory
 };
 
 // the optimiser ignores odometry edges (src/pose_graph_optimization.py:14-16, :28-30)
@@ -73,30 +73,39 @@ sgd_weights_kernel(const SgdArgs a)
     a.dW[4 * e] = w[0]; a.dW[4 * e + 1] = w[1]; a.dW[4 * e + 2] = w[2]; a.dW[4 * e + 3] = nrm;
 }
 
-__global__ void __launch_bounds__(256)
+// The per-node kernels (this one and sgd_apply_kernel) walk all E edges per node in edge order, so
+// their parallelism is the number of nodes: small CTAs (kSgdNodeThreads) put the few thousand nodes
+// of a map on as many SMs as possible, one or two warps per scheduler.
+constexpr int kSgdNodeThreads = 64;
+constexpr int kSgdNodeTile = 512;                          // edges per shared-memory tile (one global round trip each)
+
+__global__ void __launch_bounds__(kSgdNodeThreads)
 sgd_accumulate_kernel(const SgdArgs a)
 {
-    __shared__ int2 s_ab[256];
-    __shared__ double s_w[256][3];
+    __shared__ int2 s_ab[kSgdNodeTile];
+    __shared__ double s_w[kSgdNodeTile];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-    for (int e0 = 0; e0 < a.E; e0 += 256) {
-        const int e = e0 + threadIdx.x;
-        if (e < a.E) {
+    const int j = blockIdx.y;                                  // dof: one (node, dof) per thread
+    double m = 0.0;
+    for (int e0 = 0; e0 < a.E; e0 += kSgdNodeTile) {
+        for (int k = threadIdx.x; k < kSgdNodeTile && e0 + k < a.E; k += blockDim.x) {
+            const int e = e0 + k;
             int ea = a.edges[2 * e], eb = a.edges[2 * e + 1];
             if (sgd_skipped(ea, eb)) eb = ea;                  // empty range
-            s_ab[threadIdx.x] = make_int2(ea, eb);
-            s_w[threadIdx.x][0] = a.dW[4 * e]; s_w[threadIdx.x][1] = a.dW[4 * e + 1]; s_w[threadIdx.x][2] = a.dW[4 * e + 2];
+            s_ab[k] = make_int2(ea, eb);
+            s_w[k] = a.dW[4 * e + j];
         }
         __syncthreads();
-        const int cnt = min(256, a.E - e0);
+        const int cnt = min(kSgdNodeTile, a.E - e0);
+#pragma unroll 4
         for (int k = 0; k < cnt; ++k) {                        // edge order = the reference's order of additions
             const int2 ab = s_ab[k];
-            if (ab.x < i && i <= ab.y) { m0 += s_w[k][0]; m1 += s_w[k][1]; m2 += s_w[k][2]; }
+            const double q = m + s_w[k];
+            m = (ab.x < i && i <= ab.y) ? q : m;                 // select, not branch: the loads run ahead
         }
         __syncthreads();
     }
-    if (i < a.n) { a.M[3 * i] = m0; a.M[3 * i + 1] = m1; a.M[3 * i + 2] = m2; }
+    if (i < a.n) a.M[3 * i + j] = m;
 }
 
 // x mod m for m > 0 with the sign of m (np.remainder, :35).  x - floor(x/m)*m in one FMA: for
@@ -112,76 +121,42 @@ __device__ __forceinline__ double mod_pos(double x, double m, double inv_m)
     return r;
 }
 
-// what one edge needs that does not depend on the moving poses
-struct SgdEdge {
-    int ea, eb;
-    double t2, t5, phi;           // tf[0,2], tf[1,2], atan2(tf[1,0], tf[0,0])
-    double base[3], total[3], itot[3];   // P_j[a], P_j[b] - P_j[a] = sum of 1/M over (a, b] (:41), 1 / that
-};
-
-__device__ __forceinline__ void sgd_load_edge(const SgdArgs &a, int e, SgdEdge &x)
-{
-    x.ea = a.edges[2 * e]; x.eb = a.edges[2 * e + 1];
-    const double *T = a.tf + 6 * e;
-    x.t2 = T[2]; x.t5 = T[5];
-    const double *pb = a.PB + 10 * e;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { x.base[j] = pb[j]; x.total[j] = pb[3 + j]; x.itot[j] = pb[6 + j]; }
-    x.phi = pb[9];
-}
-
-// Residual and clipped step of one edge under the current poses (:33-44): beta_j / total_j and
-// beta_j, the two factors the node updates need.  This sits on the critical chain of the pass (edge
-// e+1 reads what edge e wrote), so everything that does not depend on the moving poses has been taken
-// off it, using two identities that hold to rounding (1e-16 relative; the contract is 1e-9, and the
-// goldens of the unmodified reference agree to 1e-12, tests/test_gpu_sgd.py):
+// The residual and clipped step of one edge under the current poses (:33-44) sit on the critical chain
+// of the pass (edge e+1 reads what edge e wrote), so everything that does not depend on the moving
+// poses is taken off it, using identities that hold to rounding (1e-16 relative; the contract is
+// 1e-9, and the goldens of the unmodified reference agree to 1e-12, tests/test_gpu_sgd.py):
 //   * heading of Pb_new = pose_to_mat(poses[a]) @ tf (:33-34): atan2 of a product of rotations is the
 //     sum of their angles mod 2 pi, so atan2(tf[1,0], tf[0,0]) is computed once per edge beforehand;
 //   * inv(R^T sigma R) with sigma = lcu I (:36) is I / lcu whatever R is.
-// What remains per edge: one sincos, a handful of multiply-adds, the clip, three multiplications.
-__device__ __forceinline__ void sgd_edge_step(const SgdEdge &x, const double *pose_a, const double *pose_b,
-                                              const double *alpha, double inv_lcu, double *coef, double *tot)
-{
-    const double two_pi = 6.283185307179586, inv_two_pi = 0.15915494309189535;   // 2 * np.pi
-    const double pax = pose_a[0], pay = pose_a[1], pat = pose_a[2];
-    const double pbx = pose_b[0], pby = pose_b[1], pbt = pose_b[2];
-    double s, c;
-    sincos(pat, &s, &c);
-    double r[3];
-    r[0] = (c * x.t2 + -s * x.t5 + pax) - pbx;                 // translation of Pb_new minus poses[b]
-    r[1] = (s * x.t2 + c * x.t5 + pay) - pby;
-    r[2] = mod_pos((pat + x.phi) - pbt, two_pi, inv_two_pi);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const double d = 2.0 * (inv_lcu * r[j]);                                 // :36
-        double beta = (double)(x.eb - x.ea) * d * alpha[j];                      // :42
-        if (fabs(beta) > fabs(r[j])) beta = r[j];                                // :43-44
-        coef[j] = beta * x.itot[j]; tot[j] = coef[j] * x.total[j];
-    }
-}
+// What remains per edge: one sincos, a dozen multiply-adds, the clip, three multiplications.  (The
+// heading of a moves by whole radians within a pass -- the reference never wraps the residual's
+// [0, 2 pi) back -- so there is no small-angle shortcut for the sincos.)
 
 // The host passes only edges with b > a + 1 (the others move nothing, see icpb_pose_graph_sgd).
 //
 // LAZY chain.  Edge e adds to node i > a_e the amount f_e(i) = coef_e (P[min(i, b_e)] - P[a_e]) (per
 // dof).  The only poses the chain itself ever needs are the two endpoints of the edge it is about to
-// evaluate, and pose(i) at that moment = pose0(i) + sum over the edges processed so far of f_e'(i).
-// So nothing is swept per edge: every edge leaves a 80-byte record (a, b, coef, P[a], P[b]); the
-// endpoints of the next edge are evaluated from pose0 and the records -- 480 threads take the
-// records strided, a fixed-order tree adds the partial sums -- and a separate kernel
-// (sgd_apply_kernel, one thread per node, all SMs) applies every record to every node at the end, in
-// edge order per node, which is the reference's own order of additions.  The work per edge no
-// longer depends on the number of poses, the poses never have to fit shared memory (no cluster
-// path), and the pass costs O(E^2 / 480 + E) steps on one SM plus O(N E) fully parallel work instead
-// of O(N E / 480) steps on the critical chain.
+// evaluate, and those are known before the pass starts: the 2E endpoints are the chain's *slots*.
+// Every slot carries the running pose of its node -- pose0(i) + f_0(i) + f_1(i) + ..., the reference's
+// own sequence of additions for that node -- and belongs to one thread of warps 1..15, which adds
+// every new record to the slots of the edges still to come: 2E/480 slots per thread and edge, no
+// reduction.  A separate kernel (sgd_apply_kernel, one thread per node, all SMs) applies every record
+// to every node at the end, in the same order, so the chain's endpoint values are the bits the apply
+// kernel produces for those nodes.  The work per edge does not depend on the number of poses, and the
+// poses never have to fit shared memory.
 //
-// Pipelining: warp 0 is the *scalar warp*.  While it evaluates edge e (sum of the partials the other
-// warps produced during the previous edge + the one record, e - 1, they could not yet see; sincos;
-// clip; record e), warps 1..15 already add up records 0..e-1 for the endpoints of edge e + 1.  One
-// barrier per edge.
+// Pipelining: warp 0 is the *scalar warp*.  While it evaluates edge e (published endpoint poses +
+// record e-1, which it still holds in registers; sincos; clip; record e), warps 1..15 add record e-1
+// to their slots and publish the endpoints of edge e+1.  One barrier per edge.
+//
+// (Round-2 history: a first lazy version summed all earlier records per endpoint with a warp
+// reduction per worker warp; a cycle probe showed the busiest worker, not the scalar warp, setting
+// the pace at 1,780 of 1,910 cycles per edge.)
 constexpr int kSgdThreads = 512;
 constexpr int kSgdWarps = kSgdThreads / 32;
+constexpr int kSgdOwners = kSgdThreads - 32;                   // threads that own slots (warps 1..15)
 
-struct SgdRecords {          // structure of arrays, E entries each (global memory)
+struct SgdRecords {          // structure of arrays, E entries each (global memory; read by sgd_apply_kernel)
     int2   *ab;
     double *coef, *pa, *pb;  // [3][E]
 };
@@ -207,17 +182,24 @@ __device__ __forceinline__ void sgd_add_term(int i, const double *Pi, int ra, in
 }
 
 // Everything edge e needs that does not depend on the moving poses, gathered once per pass into one
-// contiguous 184-byte struct, so that the chain only ever issues one round of independent loads per
-// edge -- and issues it one edge ahead, under the arithmetic of the current edge.
+// contiguous 184-byte struct and handed to the chain through a ring in shared memory.
 struct SgdEdgeFull {
-    double ea, eb;                // node ids (exact in a double)
+    int ea, eb;                   // node ids
+    double span;                  // (double)(eb - ea)
     double t2, t5, phi;
     double base[3], total[3], itot[3];
     double p0a[3], p0b[3];        // poses at the start of the pass
     double Pb[3];                 // P[b] (P[a] is base)
 };
-static_assert(sizeof(SgdEdgeFull) == 184, "SgdEdgeFull layout");
+constexpr int kSgdEdgeDoubles = 23;
+static_assert(sizeof(SgdEdgeFull) == 8 * kSgdEdgeDoubles, "SgdEdgeFull layout");
+// positions of the fields in the struct seen as an array of doubles (the scalar warp indexes by lane)
+enum { kEsSpan = 1, kEsT2 = 2, kEsT5 = 3, kEsPhi = 4, kEsBase = 5, kEsTotal = 8, kEsItot = 11,
+       kEsP0a = 14, kEsP0b = 17, kEsPb = 20 };
 
+
+// SLOTS_SMEM: the slots live in dynamic shared memory (13 E doubles; a.SL is unused)
+template <bool SLOTS_SMEM>
 __global__ void __launch_bounds__(kSgdThreads, 1)
 sgd_chain_kernel(const SgdArgs a)
 {
@@ -225,12 +207,20 @@ sgd_chain_kernel(const SgdArgs a)
     __shared__ int    s_beste[32];
     __shared__ double s_gamma[3];
     __shared__ double s_scan[3][kSgdThreads];
-    __shared__ double s_part[2][kSgdWarps][6];                 // per edge parity: warp partial sums, 2 nodes x 3 dofs
+    __shared__ double s_wtot[3][kSgdWarps];
+    __shared__ double s_next[2][6];                            // per edge parity: published poses of its endpoints
+    __shared__ double s_coef[2][4];                            // per edge parity: the coefficients of its record
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const SgdRecords R = sgd_records(a);
     SgdEdgeFull *ES = reinterpret_cast<SgdEdgeFull *>(a.ES);
+    // slots: endpoint q = 2 * edge + side; P of its node [3][2E], running pose [3][2E], node id [2E]
+    extern __shared__ double s_slots[];
+    const size_t S = 2 * (size_t)a.E;
+    double *sl_P = SLOTS_SMEM ? s_slots : a.SL;
+    double *sl_acc = sl_P + 3 * S;
+    int *sl_node = reinterpret_cast<int *>(sl_P + 6 * S);
 
     // ---- gamma: the first edge with the smallest |diag(W)|^2 (strict > in :23) ----
     {
@@ -265,21 +255,30 @@ sgd_chain_kernel(const SgdArgs a)
                 acc[j] += m > 0.0 ? 1.0 / m : 0.0;             // uncovered nodes never enter a range
                 a.P[3 * i + j] = acc[j];
             }
+        // exclusive scan of the slice totals over the threads in two levels, each a sequential fold in a
+        // fixed order (lane 0..2 of every warp over its 32 totals, one dof each; then the 16 warp totals)
         for (int j = 0; j < 3; ++j) s_scan[j][tid] = acc[j];
         __syncthreads();
-        if (tid < 3) {                                         // exclusive scan of the slice totals
+        if (lane < 3) {
             double run = 0.0;
-            for (int t = 0; t < NT; ++t) { const double v = s_scan[tid][t]; s_scan[tid][t] = run; run += v; }
+            for (int t = warp * 32; t < warp * 32 + 32; ++t) { const double v = s_scan[lane][t]; s_scan[lane][t] = run; run += v; }
+            s_wtot[lane][warp] = run;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double run = 0.0;
+            for (int w = 0; w < kSgdWarps; ++w) { const double v = s_wtot[tid][w]; s_wtot[tid][w] = run; run += v; }
         }
         __syncthreads();
         for (int i = i0; i < i1; ++i)
-            for (int j = 0; j < 3; ++j) a.P[3 * i + j] += s_scan[j][tid];
+            for (int j = 0; j < 3; ++j) a.P[3 * i + j] += s_wtot[j][warp] + s_scan[j][tid];
         __syncthreads();
-        // ---- per edge: everything the chain needs, in one struct; the static part of its record ----
+        // ---- per edge: everything the chain needs in one struct, the static part of its record, its
+        // two slots (running pose = the pose at the start of the pass) ----
         for (int e = tid; e < a.E; e += NT) {
             const int ea = a.edges[2 * e], eb = a.edges[2 * e + 1];
             SgdEdgeFull x;
-            x.ea = (double)ea; x.eb = (double)eb;
+            x.ea = ea; x.eb = eb; x.span = (double)(eb - ea);
             x.t2 = a.tf[6 * e + 2]; x.t5 = a.tf[6 * e + 5];
             x.phi = atan2(a.tf[6 * e + 3], a.tf[6 * e]);
             for (int j = 0; j < 3; ++j) {
@@ -287,9 +286,14 @@ sgd_chain_kernel(const SgdArgs a)
                 x.base[j] = pa; x.total[j] = tot; x.itot[j] = 1.0 / tot; x.Pb[j] = pb;
                 x.p0a[j] = a.poses[3 * ea + j]; x.p0b[j] = a.poses[3 * eb + j];
                 R.pa[j * (size_t)a.E + e] = pa; R.pb[j * (size_t)a.E + e] = pb;
+                sl_P[j * S + 2 * e] = pa; sl_P[j * S + 2 * e + 1] = pb;
+                sl_acc[j * S + 2 * e] = x.p0a[j]; sl_acc[j * S + 2 * e + 1] = x.p0b[j];
             }
+            sl_node[2 * e] = ea; sl_node[2 * e + 1] = eb;
             ES[e] = x;
             R.ab[e] = make_int2(ea, eb);
+            if (e == 0)
+                for (int j = 0; j < 3; ++j) { s_next[0][j] = x.p0a[j]; s_next[0][3 + j] = x.p0b[j]; }
         }
     }
     __syncthreads();
@@ -299,130 +303,152 @@ sgd_chain_kernel(const SgdArgs a)
     const double inv_lcu = 1.0 / a.lcu;
 
     if (a.E == 0) return;
-    // The edge structs reach the chain through a 4-slot ring in shared memory that the last warp (idle
-    // otherwise) fills two edges ahead: lane k copies double k of the 184-byte struct, one coalesced
-    // load per edge, off everybody's critical path.
+    // The edge structs reach the scalar warp through a 4-slot ring in shared memory that the last warp
+    // fills two edges ahead: lane k copies double k of the 184-byte struct, one coalesced load per edge.
+    // The load is issued one iteration before its store (an L2 round trip is longer than an edge).
     __shared__ SgdEdgeFull s_es[4];
-    if (warp == kSgdWarps - 1 && lane < 23)
+    double es_staged = 0.0;                                    // double `lane` of the struct of edge e + 2
+    if (warp == kSgdWarps - 1 && lane < kSgdEdgeDoubles) {
         for (int k = 0; k < 2 && k < a.E; ++k)
             reinterpret_cast<double *>(&s_es[k])[lane] = reinterpret_cast<const double *>(ES + k)[lane];
+        if (2 < a.E) es_staged = reinterpret_cast<const double *>(ES + 2)[lane];
+    }
     __syncthreads();
-    double last_coef[3] = {0.0, 0.0, 0.0};                     // warp 0: record e - 1, the one the partials lack
-    double last_pa[3] = {0.0, 0.0, 0.0}, last_pb[3] = {0.0, 0.0, 0.0};
+    // Scalar warp, lane-parallel: lane l < 6 carries dof j = l % 3 of endpoint side = l / 3 (0: a, 1: b);
+    // lanes 0..2 go on to the residual and step of dof j.  Lanes >= 6 shadow lane 5.
+    const int l6 = min(lane, 5), side = l6 / 3, dof = l6 - 3 * side;
+    const double alpha_l = dof == 0 ? alpha[0] : (dof == 1 ? alpha[1] : alpha[2]);
+    double last_coef = 0.0;                                    // record e - 1 (the one the slots lack), dof of this lane
     int last_a = 0x7fffffff, last_b = 0;
+    const int own = tid - 32;                                  // slots own, own + 480, ... (warps 1..15)
+#ifdef ICPB_SGD_PROBE
+    const long long pr_begin = clock64();
+#endif
     for (int e = 0; e < a.E; ++e) {
-        // Worker warps: as many as keep every lane at <= 4 records (the partial sums over e records cost
-        // one warp reduction per worker, and all 16 warps share one SM's issue slots with the scalar
-        // warp: with 534 edges, 15 workers made the pass issue-bound at 2,700 cycles per edge)
-        const int workers = min(kSgdWarps - 2, max(1, (e + 127) / 128));
-        if (warp == kSgdWarps - 1) {
-            if (lane < 23 && e + 2 < a.E)                        // slot (e + 2) % 4 was last read in iteration e - 1
-                reinterpret_cast<double *>(&s_es[(e + 2) & 3])[lane] = reinterpret_cast<const double *>(ES + e + 2)[lane];
-        } else if (warp == 0) {
-            const SgdEdgeFull &cur = s_es[e & 3];
-            // ---- evaluate edge e: its endpoints = start-of-pass poses + the partial sums over records
-            // 0..e-2 (warps 1..15, previous iteration) + record e-1 (kept in registers) ----
-            const int ea = (int)cur.ea, eb = (int)cur.eb;
-            double pose_a[3], pose_b[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { pose_a[j] = cur.p0a[j]; pose_b[j] = cur.p0b[j]; }
-            if (e > 0) {
-                // second stage of the tree: lane k < 6 adds value k of the workers' partials, in warp order
-                // (the workers of the previous iteration: the same formula with e - 1)
-                const int prev_workers = min(kSgdWarps - 2, max(1, (e - 1 + 127) / 128));
-                double v = 0.0;
-                if (lane < 6)
-                    for (int w = 1; w <= prev_workers; ++w) v += s_part[e & 1][w][lane];
-                double sa[3], sb[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    sa[j] = __shfl_sync(0xffffffffu, v, j);
-                    sb[j] = __shfl_sync(0xffffffffu, v, 3 + j);
-                }
-                sgd_add_term(ea, cur.base, last_a, last_b, last_coef, last_pa, last_pb, sa);
-                sgd_add_term(eb, cur.Pb, last_a, last_b, last_coef, last_pa, last_pb, sb);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) { pose_a[j] += sa[j]; pose_b[j] += sb[j]; }
+        if (warp == 0) {
+            const SgdEdgeFull &ce = s_es[e & 3];
+            const double *cur = reinterpret_cast<const double *>(&ce);
+            const double *prev = reinterpret_cast<const double *>(&s_es[(e + 3) & 3]);   // edge e - 1, still in the ring
+            // ---- the endpoints of edge e: the published running poses (records 0..e-2) + record e-1 ----
+            const int ea = ce.ea, eb = ce.eb;
+            const int node = side ? eb : ea;
+            const double Pn = cur[(side ? kEsPb : kEsBase) + dof];
+            double pose = s_next[e & 1][l6];
+            {
+                const double v = (node <= last_b ? Pn : prev[kEsPb + dof]) - prev[kEsBase + dof];
+                const double q = __dadd_rn(pose, __dmul_rn(last_coef, v));
+                pose = node > last_a ? q : pose;
             }
-            SgdEdge x;
-            x.ea = ea; x.eb = eb; x.t2 = cur.t2; x.t5 = cur.t5; x.phi = cur.phi;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { x.base[j] = cur.base[j]; x.total[j] = cur.total[j]; x.itot[j] = cur.itot[j]; }
-            double coef[3], tot[3];
-            sgd_edge_step(x, pose_a, pose_b, alpha, inv_lcu, coef, tot);
-            if (lane < 3) R.coef[lane * (size_t)a.E + e] = coef[lane];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { last_coef[j] = coef[j]; last_pa[j] = cur.base[j]; last_pb[j] = cur.Pb[j]; }
+            // ---- residual (:33-35) ----
+            const double pat = __shfl_sync(0xffffffffu, pose, 2);          // heading of a
+            const double pb_v = __shfl_down_sync(0xffffffffu, pose, 3);    // lane j < 3: dof j of b
+            double sn, cs;
+            sincos(pat, &sn, &cs);
+            const double two_pi = 6.283185307179586, inv_two_pi = 0.15915494309189535;   // 2 * np.pi
+            const double u = dof == 0 ? cs : sn, v = dof == 0 ? -sn : cs;
+            const double r_lin = (u * cur[kEsT2] + v * cur[kEsT5] + pose) - pb_v;   // translation of Pb_new minus poses[b]
+            const double r_ang = mod_pos((pose + cur[kEsPhi]) - pb_v, two_pi, inv_two_pi);
+            const double r = dof == 2 ? r_ang : r_lin;
+            // ---- clipped step (:36-44) ----
+            const double dd = 2.0 * (inv_lcu * r);                                   // :36
+            double beta = cur[kEsSpan] * dd * alpha_l;                               // :42
+            if (fabs(beta) > fabs(r)) beta = r;                                      // :43-44
+            const double coef = beta * cur[kEsItot + dof];
+            if (lane < 3) {
+                s_coef[e & 1][lane] = coef;
+                R.coef[lane * (size_t)a.E + e] = coef;                   // for sgd_apply_kernel
+            }
+            last_coef = __shfl_sync(0xffffffffu, coef, dof);
             last_a = ea; last_b = eb;
-        } else if (e + 1 < a.E && warp <= workers) {
-            // ---- partial sums for the endpoints of edge e+1 over records 0..e-1 (all complete) ----
-            const SgdEdgeFull &cur = s_es[(e + 1) & 3];
-            const int na = (int)cur.ea, nb = (int)cur.eb;
-            double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int r = tid - 32; r < e; r += 32 * workers) {
-                const int2 ab = R.ab[r];
-                double coef[3], pa[3], pb[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    coef[j] = R.coef[j * (size_t)a.E + r]; pa[j] = R.pa[j * (size_t)a.E + r]; pb[j] = R.pb[j * (size_t)a.E + r];
-                }
-                sgd_add_term(na, cur.base, ab.x, ab.y, coef, pa, pb, acc);
-                sgd_add_term(nb, cur.Pb, ab.x, ab.y, coef, pa, pb, acc + 3);
+        } else {
+            if (warp == kSgdWarps - 1 && lane < kSgdEdgeDoubles && e + 2 < a.E) {
+                // ring slot (e + 2) % 4 was last read in iteration e - 1 (as the previous edge of e - 1's successor)
+                reinterpret_cast<double *>(&s_es[(e + 2) & 3])[lane] = es_staged;
+                if (e + 3 < a.E) es_staged = reinterpret_cast<const double *>(ES + e + 3)[lane];
             }
+            if (e + 1 < a.E) {
+                // ---- record e-1 into the slots of the edges still to come (edge e+1 onwards); the owners
+                // of the endpoints of edge e+1 publish them ----
+                const int q_first = 2 * (e + 1);
+                int q = own;
+                if (q < q_first) q += (q_first - q + kSgdOwners - 1) / kSgdOwners * kSgdOwners;
+                if (e >= 1) {
+                    const SgdEdgeFull &re = s_es[(e + 3) & 3];     // edge e - 1: still in the ring
+                    const int ra = re.ea, rb = re.eb;
+                    double rc[3], rpa[3], rpb[3];
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-            if (lane < 6) {
-                double v = acc[0];
+                    for (int j = 0; j < 3; ++j) { rc[j] = s_coef[(e - 1) & 1][j]; rpa[j] = re.base[j]; rpb[j] = re.Pb[j]; }
+                    // two slots per round, every load before the first store: the compiler cannot tell
+                    // that the slot arrays do not overlap and would run the dofs and slots one after another
+                    for (int qq = q; qq < (int)S; qq += 2 * kSgdOwners) {
+                        const int q2 = qq + kSgdOwners;
+                        const bool two = q2 < (int)S;
+                        const int i1 = sl_node[qq], i2 = two ? sl_node[q2] : 0;
+                        const bool on1 = i1 > ra, on2 = two && i2 > ra;
+                        double pv1[3], av1[3], pv2[3], av2[3];
 #pragma unroll
-                for (int k = 1; k < 6; ++k) v = lane == k ? acc[k] : v;
-                s_part[(e + 1) & 1][warp][lane] = v;
+                        for (int j = 0; j < 3; ++j) {
+                            if (on1) { pv1[j] = sl_P[j * S + qq]; av1[j] = sl_acc[j * S + qq]; }
+                            if (on2) { pv2[j] = sl_P[j * S + q2]; av2[j] = sl_acc[j * S + q2]; }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (on1) av1[j] = __dadd_rn(av1[j], __dmul_rn(rc[j], (i1 <= rb ? pv1[j] : rpb[j]) - rpa[j]));
+                            if (on2) av2[j] = __dadd_rn(av2[j], __dmul_rn(rc[j], (i2 <= rb ? pv2[j] : rpb[j]) - rpa[j]));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (on1) sl_acc[j * S + qq] = av1[j];
+                            if (on2) sl_acc[j * S + q2] = av2[j];
+                        }
+                    }
+                }
+                if (q <= q_first + 1) {                          // q is q_first or q_first + 1: this thread owns it
+                    const int sd = q - q_first;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) s_next[(e + 1) & 1][3 * sd + j] = sl_acc[j * S + q];
+                }
             }
         }
-        __syncthreads();           // record e, the partials for edge e+1 and the struct of edge e+2 are visible
+        __syncthreads();           // record e, the endpoints of edge e+1 and the struct of edge e+2 are visible
     }
+#ifdef ICPB_SGD_PROBE
+    if (tid == 0) printf("sgd probe: loop %lld cycles, E %d\n", clock64() - pr_begin, a.E);
+#endif
 }
 
 // Every record applied to every node, in edge order per node: pose(i) += f_0(i), += f_1(i), ... --
 // the reference's own sequence of additions for that node (:45-48).  One thread per node.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSgdNodeThreads)
 sgd_apply_kernel(const SgdArgs a)
 {
-    __shared__ int2 s_ab[128];
-    __shared__ double s_c[3][128], s_pa[3][128], s_pb[3][128];
+    __shared__ int2 s_ab[kSgdNodeTile];
+    __shared__ double s_c[kSgdNodeTile], s_pa[kSgdNodeTile], s_pb[kSgdNodeTile];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;                                  // dof: one (node, dof) per thread
     const SgdRecords R = sgd_records(a);
-    double p[3] = {0.0, 0.0, 0.0}, Pi[3] = {0.0, 0.0, 0.0};
-    if (i < a.n) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { p[j] = a.poses[3 * i + j]; Pi[j] = a.P[3 * i + j]; }
-    }
-    for (int e0 = 0; e0 < a.E; e0 += 128) {                     // the records stream through shared memory
-        const int cnt = min(128, a.E - e0);
-        for (int k = threadIdx.x; k < cnt; k += blockDim.x) s_ab[k] = R.ab[e0 + k];
-        for (int k = threadIdx.x; k < 3 * cnt; k += blockDim.x) {
-            const int j = k / cnt, r = k - j * cnt;
-            s_c[j][r] = R.coef[j * (size_t)a.E + e0 + r];
-            s_pa[j][r] = R.pa[j * (size_t)a.E + e0 + r];
-            s_pb[j][r] = R.pb[j * (size_t)a.E + e0 + r];
+    const double *Rc = R.coef + j * (size_t)a.E, *Rpa = R.pa + j * (size_t)a.E, *Rpb = R.pb + j * (size_t)a.E;
+    double p = 0.0, Pi = 0.0;
+    if (i < a.n) { p = a.poses[3 * i + j]; Pi = a.P[3 * i + j]; }
+    for (int e0 = 0; e0 < a.E; e0 += kSgdNodeTile) {            // the records stream through shared memory
+        const int cnt = min(kSgdNodeTile, a.E - e0);
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            s_ab[k] = R.ab[e0 + k];
+            s_c[k] = Rc[e0 + k]; s_pa[k] = Rpa[e0 + k]; s_pb[k] = Rpb[e0 + k];
         }
         __syncthreads();
-        for (int k = 0; k < cnt; ++k) {                         // edge order = the reference's order of additions
+        // edge order = the reference's order of additions.  Branch-free and unrolled: the terms do not
+        // depend on p, so only one addition and one select per record sit on the dependent chain
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
             const int2 ab = s_ab[k];
-            if (i > ab.x) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double v = (i <= ab.y ? Pi[j] : s_pb[j][k]) - s_pa[j][k];
-                    p[j] = __dadd_rn(p[j], __dmul_rn(s_c[j][k], v));
-                }
-            }
+            const double v = (i <= ab.y ? Pi : s_pb[k]) - s_pa[k];
+            const double q = __dadd_rn(p, __dmul_rn(s_c[k], v));
+            p = i > ab.x ? q : p;                                // nodes up to a are not touched
         }
         __syncthreads();
     }
-    if (i < a.n) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) a.poses[3 * i + j] = p[j];
-    }
+    if (i < a.n) a.poses[3 * i + j] = p;
 }
 
 }  // namespace icpb

@@ -73,7 +73,8 @@ def test_multi_step_call_equals_the_reference_loop():
     assert slam_oracle.ate(z["corrected"], z["optimised"]) > 1e-3
 
 
-@pytest.mark.parametrize("n,n_loops,seed", [(300, 40, 1), (3000, 400, 2), (12000, 300, 3), (80000, 60, 4)])
+@pytest.mark.parametrize("n,n_loops,seed", [(300, 40, 1), (3000, 400, 2), (12000, 300, 3), (80000, 60, 4),
+                                              (4000, 2200, 5)])    # last: slots beyond shared memory
 def test_random_graphs_against_the_oracle(n, n_loops, seed):
     """Larger graphs against the numpy restatement, itself pinned to the reference by
     tests/test_sgd_oracle.py (the sequential part of a pass works on per-edge records, so the number of
