@@ -284,7 +284,6 @@ struct icpb_ctx {
     int device = 0;
     int sm_count = 0;
     int smem_limit = 0;                             // dynamic shared memory an alignment launch may ask for
-    int sgd_smem_limit = 0;                         // ... and the SGD chain kernel (its records)
     // scan table
     const double *xy = nullptr;
     const int64_t *offsets = nullptr;
@@ -574,14 +573,6 @@ int icpb_create(int device, icpb_handle *out)
         const int lim = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         if (lim < h->smem_limit) h->smem_limit = lim;
-    }
-    if (e == cudaSuccess) {
-        cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, icpb::sgd_chain_kernel<true>);
-        if (e == cudaSuccess) {
-            h->sgd_smem_limit = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
-            e = cudaFuncSetAttribute(icpb::sgd_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sgd_smem_limit);
-        }
     }
     if (e == cudaSuccess) e = cudaMalloc(&h->arrived_dev, sizeof(int32_t));
     if (e == cudaSuccess) e = cudaHostAlloc(&h->seg_vals_pinned, sizeof(int32_t) * (kMaxSegments + 1), cudaHostAllocDefault);
@@ -1534,23 +1525,20 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
     if (ve.empty() || n_steps == 0) return 0;
     ON_DEVICE(h);
     const size_t E = ve.size() / 2, N = (size_t)n;
-    // [poses 3N | tf 6E | dW 4E | SL 13E | REC 10E | ES 23E | M 3N | P 3N] doubles, then [edges 2E] int32
-    const size_t n_dbl = 3 * N + 6 * E + 4 * E + 13 * E + 10 * E + 23 * E + 3 * N + 3 * N;
+    // [RECA 10E | tf 6E | dW 4E | REC 10E | ES 23E | poses 3N | M 3N | P 3N] doubles, then [edges 2E] int32
+    // (RECA first: its 80-byte records are read as 16-byte pairs)
+    const size_t n_dbl = 10 * E + 6 * E + 4 * E + 10 * E + 23 * E + 3 * N + 3 * N + 3 * N;
     int rc;
     if ((rc = h->s_sgd.reserve(sizeof(double) * n_dbl + sizeof(int32_t) * 2 * E))) return rc;
-    double *d_poses = (double *)h->s_sgd.p, *d_tf = d_poses + 3 * N, *d_dW = d_tf + 6 * E, *d_PB = d_dW + 4 * E;
-    double *d_REC = d_PB + 13 * E, *d_ES = d_REC + 10 * E, *d_M = d_ES + 23 * E, *d_P = d_M + 3 * N;
+    double *d_RECA = (double *)h->s_sgd.p, *d_tf = d_RECA + 10 * E, *d_dW = d_tf + 6 * E;
+    double *d_REC = d_dW + 4 * E, *d_ES = d_REC + 10 * E, *d_poses = d_ES + 23 * E, *d_M = d_poses + 3 * N, *d_P = d_M + 3 * N;
     int32_t *d_edges = (int32_t *)(d_P + 3 * N);
     CU(cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_tf, vt.data(), sizeof(double) * 6 * E, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_edges, ve.data(), sizeof(int32_t) * 2 * E, cudaMemcpyHostToDevice, h->stream));
     icpb::SgdArgs a;
     a.poses = d_poses; a.edges = d_edges; a.tf = d_tf; a.n = (int32_t)n; a.E = (int32_t)E;
-    a.lcu = loop_closure_uncertainty; a.dW = d_dW; a.SL = d_PB; a.REC = d_REC; a.ES = d_ES; a.M = d_M; a.P = d_P;
-    // the chain keeps its slots (13 doubles per edge) in shared memory when they fit next to its static
-    // buffers (about 2,000 edges), else in global memory
-    const size_t slot_bytes = sizeof(double) * 13 * E;
-    const bool slots_in_smem = slot_bytes <= (size_t)h->sgd_smem_limit;
+    a.lcu = loop_closure_uncertainty; a.dW = d_dW; a.REC = d_REC; a.RECA = d_RECA; a.ES = d_ES; a.M = d_M; a.P = d_P;
     // per pass: weights of the edges, their sum per node, the lazy chain over the edges on one SM (the
     // only sequential part), then every record applied to every node on all SMs
     const dim3 node_grid((unsigned)((N + icpb::kSgdNodeThreads - 1) / icpb::kSgdNodeThreads), 3);   // (nodes, dof)
@@ -1558,8 +1546,7 @@ int icpb_pose_graph_sgd(icpb_handle h, double *h_poses, int64_t n, const int32_t
         a.learning_rate = h_learning_rates[k];
         icpb::sgd_weights_kernel<<<(unsigned)((E + 255) / 256), 256, 0, h->stream>>>(a);
         icpb::sgd_accumulate_kernel<<<node_grid, icpb::kSgdNodeThreads, 0, h->stream>>>(a);
-        if (slots_in_smem) icpb::sgd_chain_kernel<true><<<1, icpb::kSgdThreads, slot_bytes, h->stream>>>(a);
-        else icpb::sgd_chain_kernel<false><<<1, icpb::kSgdThreads, 0, h->stream>>>(a);
+        icpb::sgd_chain_kernel<<<1, icpb::kSgdThreads, 0, h->stream>>>(a);
         icpb::sgd_apply_kernel<<<node_grid, icpb::kSgdNodeThreads, 0, h->stream>>>(a);
         CU(cudaGetLastError());
     }

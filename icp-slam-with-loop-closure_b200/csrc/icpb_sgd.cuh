@@ -39,8 +39,8 @@ struct SgdArgs {
     double        *M;         // n x 3 scratch: weights
     double        *P;         // n x 3 scratch: inclusive prefix sums of 1/M
     double        *REC;       // E x 10 scratch: the per-edge records of the lazy chain (SgdRecords)
+    double        *RECA;      // E x 10 scratch: the same records as an array of structs (the chain's catch-up bursts)
     double        *ES;        // E x 23 scratch: the per-edge inputs of the chain (SgdEdgeFull)
-    double        *SL;        // E x 13 scratch: the chain's slots when they do not fit shared memory
 };
 
 // the optimiser ignores odometry edges (src/pose_graph_optimization.py:14-16, :28-30)
@@ -137,24 +137,35 @@ __device__ __forceinline__ double mod_pos(double x, double m, double inv_m)
 // LAZY chain.  Edge e adds to node i > a_e the amount f_e(i) = coef_e (P[min(i, b_e)] - P[a_e]) (per
 // dof).  The only poses the chain itself ever needs are the two endpoints of the edge it is about to
 // evaluate, and those are known before the pass starts: the 2E endpoints are the chain's *slots*.
-// Every slot carries the running pose of its node -- pose0(i) + f_0(i) + f_1(i) + ..., the reference's
-// own sequence of additions for that node -- and belongs to one thread of warps 1..15, which adds
-// every new record to the slots of the edges still to come: 2E/480 slots per thread and edge, no
-// reduction.  A separate kernel (sgd_apply_kernel, one thread per node, all SMs) applies every record
-// to every node at the end, in the same order, so the chain's endpoint values are the bits the apply
-// kernel produces for those nodes.  The work per edge does not depend on the number of poses, and the
-// poses never have to fit shared memory.
+// A slot carries the running pose of its node -- pose0(i) + f_0(i) + f_1(i) + ..., the reference's
+// own sequence of additions for that node.  A separate kernel (sgd_apply_kernel, all SMs) applies
+// every record to every node at the end, in the same order, so the chain's endpoint values are the
+// bits the apply kernel produces for those nodes.  The work per edge does not depend on the number
+// of poses, and neither the poses nor the slots have to fit shared memory.
+//
+// Slots live in REGISTERS.  The edges are cut into blocks of kSgdBlock = 240; a block has 480 slots,
+// one per thread of warps 1..15, and a thread holds two: its slot of the block the chain is in and of
+// the next one.  Every iteration the owners add the newest record to both (two slots x three dofs,
+// no memory traffic but the record) and the owners of the next edge's endpoints publish them.  When
+// the chain enters a new block, every owner loads its slot of the block after it and catches it up
+// on all records so far in one burst -- records stream through L1 as broadcast loads of 16-byte
+// pairs from an array of 80-byte records, the running pose stays in registers.  Total work
+// O(E^2 / 480) like any lazy scheme, but no reductions and no per-edge memory round trips, any E.
+// (Spreading the catch-up over the iterations of the block instead -- a few records per edge -- lost:
+// every iteration then waits for an L2 round trip that the burst amortises over hundreds of records.)
 //
 // Pipelining: warp 0 is the *scalar warp*.  While it evaluates edge e (published endpoint poses +
-// record e-1, which it still holds in registers; sincos; clip; record e), warps 1..15 add record e-1
-// to their slots and publish the endpoints of edge e+1.  One barrier per edge.
+// record e-1, which the slots did not have yet when they were published; sincos; clip; record e),
+// warps 1..15 add record e-1 to their slots and publish the endpoints of edge e+1.  One barrier per edge.
 //
-// (Round-2 history: a first lazy version summed all earlier records per endpoint with a warp
-// reduction per worker warp; a cycle probe showed the busiest worker, not the scalar warp, setting
-// the pace at 1,780 of 1,910 cycles per edge.)
+// (Round-2 history, measured with a cycle probe: a first lazy version summed all earlier records per
+// endpoint with a warp reduction per worker warp -- the busiest worker, not the scalar warp, set the
+// pace at 1,780 of 1,910 cycles per edge; slots in shared / global memory: 1,100 cycles per edge up
+// to 2,000 edges and 4.3 us per edge beyond.)
 constexpr int kSgdThreads = 512;
 constexpr int kSgdWarps = kSgdThreads / 32;
 constexpr int kSgdOwners = kSgdThreads - 32;                   // threads that own slots (warps 1..15)
+constexpr int kSgdBlock = kSgdOwners / 2;                      // edges per block: one slot per owner and block
 
 struct SgdRecords {          // structure of arrays, E entries each (global memory; read by sgd_apply_kernel)
     int2   *ab;
@@ -198,8 +209,6 @@ enum { kEsSpan = 1, kEsT2 = 2, kEsT5 = 3, kEsPhi = 4, kEsBase = 5, kEsTotal = 8,
        kEsP0a = 14, kEsP0b = 17, kEsPb = 20 };
 
 
-// SLOTS_SMEM: the slots live in dynamic shared memory (13 E doubles; a.SL is unused)
-template <bool SLOTS_SMEM>
 __global__ void __launch_bounds__(kSgdThreads, 1)
 sgd_chain_kernel(const SgdArgs a)
 {
@@ -215,12 +224,6 @@ sgd_chain_kernel(const SgdArgs a)
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const SgdRecords R = sgd_records(a);
     SgdEdgeFull *ES = reinterpret_cast<SgdEdgeFull *>(a.ES);
-    // slots: endpoint q = 2 * edge + side; P of its node [3][2E], running pose [3][2E], node id [2E]
-    extern __shared__ double s_slots[];
-    const size_t S = 2 * (size_t)a.E;
-    double *sl_P = SLOTS_SMEM ? s_slots : a.SL;
-    double *sl_acc = sl_P + 3 * S;
-    int *sl_node = reinterpret_cast<int *>(sl_P + 6 * S);
 
     // ---- gamma: the first edge with the smallest |diag(W)|^2 (strict > in :23) ----
     {
@@ -273,8 +276,7 @@ sgd_chain_kernel(const SgdArgs a)
         for (int i = i0; i < i1; ++i)
             for (int j = 0; j < 3; ++j) a.P[3 * i + j] += s_wtot[j][warp] + s_scan[j][tid];
         __syncthreads();
-        // ---- per edge: everything the chain needs in one struct, the static part of its record, its
-        // two slots (running pose = the pose at the start of the pass) ----
+        // ---- per edge: everything the chain needs in one struct, the static part of its record ----
         for (int e = tid; e < a.E; e += NT) {
             const int ea = a.edges[2 * e], eb = a.edges[2 * e + 1];
             SgdEdgeFull x;
@@ -286,12 +288,12 @@ sgd_chain_kernel(const SgdArgs a)
                 x.base[j] = pa; x.total[j] = tot; x.itot[j] = 1.0 / tot; x.Pb[j] = pb;
                 x.p0a[j] = a.poses[3 * ea + j]; x.p0b[j] = a.poses[3 * eb + j];
                 R.pa[j * (size_t)a.E + e] = pa; R.pb[j * (size_t)a.E + e] = pb;
-                sl_P[j * S + 2 * e] = pa; sl_P[j * S + 2 * e + 1] = pb;
-                sl_acc[j * S + 2 * e] = x.p0a[j]; sl_acc[j * S + 2 * e + 1] = x.p0b[j];
             }
-            sl_node[2 * e] = ea; sl_node[2 * e + 1] = eb;
             ES[e] = x;
             R.ab[e] = make_int2(ea, eb);
+            double *ra = a.RECA + 10 * (size_t)e;                // {coef[3] (written by the chain), pa[3], pb[3], (a, b)}
+            for (int j = 0; j < 3; ++j) { ra[3 + j] = x.base[j]; ra[6 + j] = x.Pb[j]; }
+            reinterpret_cast<int2 *>(ra)[9] = make_int2(ea, eb);
             if (e == 0)
                 for (int j = 0; j < 3; ++j) { s_next[0][j] = x.p0a[j]; s_next[0][3 + j] = x.p0b[j]; }
         }
@@ -320,7 +322,24 @@ sgd_chain_kernel(const SgdArgs a)
     const double alpha_l = dof == 0 ? alpha[0] : (dof == 1 ? alpha[1] : alpha[2]);
     double last_coef = 0.0;                                    // record e - 1 (the one the slots lack), dof of this lane
     int last_a = 0x7fffffff, last_b = 0;
-    const int own = tid - 32;                                  // slots own, own + 480, ... (warps 1..15)
+    // slot owners (warps 1..15): thread `own` holds endpoint `own & 1` of edge `own >> 1` of a block
+    const int own = tid - 32, s_off = own >> 1, s_side = own & 1;
+    int cur_node = -1, nxt_node = -1;                          // -1: no slot (block past the last edge)
+    double cur_P[3], cur_acc[3], nxt_P[3], nxt_acc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { cur_P[j] = cur_acc[j] = nxt_P[j] = nxt_acc[j] = 0.0; }
+    auto slot_load = [&](int edge, int &node, double *P, double *acc) {
+        node = -1;
+        if (warp >= 1 && edge < a.E) {
+            const SgdEdgeFull &x = ES[edge];
+            node = s_side ? x.eb : x.ea;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { P[j] = s_side ? x.Pb[j] : x.base[j]; acc[j] = s_side ? x.p0b[j] : x.p0a[j]; }
+        }
+    };
+    slot_load(s_off, cur_node, cur_P, cur_acc);
+    slot_load(kSgdBlock + s_off, nxt_node, nxt_P, nxt_acc);
+    int blk_first = 0;                                         // first edge of the block the chain is in
 #ifdef ICPB_SGD_PROBE
     const long long pr_begin = clock64();
 #endif
@@ -357,6 +376,7 @@ sgd_chain_kernel(const SgdArgs a)
             if (lane < 3) {
                 s_coef[e & 1][lane] = coef;
                 R.coef[lane * (size_t)a.E + e] = coef;                   // for sgd_apply_kernel
+                a.RECA[10 * (size_t)e + lane] = coef;                    // for the catch-up bursts
             }
             last_coef = __shfl_sync(0xffffffffu, coef, dof);
             last_a = ea; last_b = eb;
@@ -366,47 +386,50 @@ sgd_chain_kernel(const SgdArgs a)
                 reinterpret_cast<double *>(&s_es[(e + 2) & 3])[lane] = es_staged;
                 if (e + 3 < a.E) es_staged = reinterpret_cast<const double *>(ES + e + 3)[lane];
             }
-            if (e + 1 < a.E) {
-                // ---- record e-1 into the slots of the edges still to come (edge e+1 onwards); the owners
-                // of the endpoints of edge e+1 publish them ----
-                const int q_first = 2 * (e + 1);
-                int q = own;
-                if (q < q_first) q += (q_first - q + kSgdOwners - 1) / kSgdOwners * kSgdOwners;
-                if (e >= 1) {
-                    const SgdEdgeFull &re = s_es[(e + 3) & 3];     // edge e - 1: still in the ring
-                    const int ra = re.ea, rb = re.eb;
-                    double rc[3], rpa[3], rpb[3];
+            if (e == blk_first + kSgdBlock) {
+                // ---- the chain enters the next block: its slots move up, the slots of the block after it
+                // are loaded and caught up on the records 0..e-2 (record e-1 follows below, as for all).
+                // Same address in every thread: broadcast loads of five 16-byte pairs per record ----
+                blk_first += kSgdBlock;
+                cur_node = nxt_node;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) { rc[j] = s_coef[(e - 1) & 1][j]; rpa[j] = re.base[j]; rpb[j] = re.Pb[j]; }
-                    // two slots per round, every load before the first store: the compiler cannot tell
-                    // that the slot arrays do not overlap and would run the dofs and slots one after another
-                    for (int qq = q; qq < (int)S; qq += 2 * kSgdOwners) {
-                        const int q2 = qq + kSgdOwners;
-                        const bool two = q2 < (int)S;
-                        const int i1 = sl_node[qq], i2 = two ? sl_node[q2] : 0;
-                        const bool on1 = i1 > ra, on2 = two && i2 > ra;
-                        double pv1[3], av1[3], pv2[3], av2[3];
+                for (int j = 0; j < 3; ++j) { cur_P[j] = nxt_P[j]; cur_acc[j] = nxt_acc[j]; }
+                slot_load(blk_first + kSgdBlock + s_off, nxt_node, nxt_P, nxt_acc);
+                if (nxt_node >= 0) {
+#pragma unroll 4
+                    for (int r = 0; r < e - 1; ++r) {
+                        const double2 *rec = reinterpret_cast<const double2 *>(a.RECA + 10 * (size_t)r);
+                        const double2 v0 = rec[0], v1 = rec[1], v2 = rec[2], v3 = rec[3], v4 = rec[4];
+                        const double rc[3] = {v0.x, v0.y, v1.x}, rpa[3] = {v1.y, v2.x, v2.y}, rpb[3] = {v3.x, v3.y, v4.x};
+                        const int ra = __double2loint(v4.y), rb = __double2hiint(v4.y);
+                        const bool on = nxt_node > ra, inside = nxt_node <= rb;
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
-                            if (on1) { pv1[j] = sl_P[j * S + qq]; av1[j] = sl_acc[j * S + qq]; }
-                            if (on2) { pv2[j] = sl_P[j * S + q2]; av2[j] = sl_acc[j * S + q2]; }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            if (on1) av1[j] = __dadd_rn(av1[j], __dmul_rn(rc[j], (i1 <= rb ? pv1[j] : rpb[j]) - rpa[j]));
-                            if (on2) av2[j] = __dadd_rn(av2[j], __dmul_rn(rc[j], (i2 <= rb ? pv2[j] : rpb[j]) - rpa[j]));
-                        }
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            if (on1) sl_acc[j * S + qq] = av1[j];
-                            if (on2) sl_acc[j * S + q2] = av2[j];
+                            const double q = __dadd_rn(nxt_acc[j], __dmul_rn(rc[j], (inside ? nxt_P[j] : rpb[j]) - rpa[j]));
+                            nxt_acc[j] = on ? q : nxt_acc[j];
                         }
                     }
                 }
-                if (q <= q_first + 1) {                          // q is q_first or q_first + 1: this thread owns it
-                    const int sd = q - q_first;
+            }
+            if (e + 1 < a.E) {
+                // ---- record e-1 into both slots; the owners of the endpoints of edge e+1 publish them ----
+                if (e >= 1) {
+                    const SgdEdgeFull &re = s_es[(e + 3) & 3];     // edge e - 1: still in the ring
+                    const int ra = re.ea, rb = re.eb;
+                    const bool on_c = cur_node > ra, in_c = cur_node <= rb, on_n = nxt_node > ra, in_n = nxt_node <= rb;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) s_next[(e + 1) & 1][3 * sd + j] = sl_acc[j * S + q];
+                    for (int j = 0; j < 3; ++j) {
+                        const double rc = s_coef[(e - 1) & 1][j], rpa = re.base[j], rpb = re.Pb[j];
+                        const double qc = __dadd_rn(cur_acc[j], __dmul_rn(rc, (in_c ? cur_P[j] : rpb) - rpa));
+                        const double qn = __dadd_rn(nxt_acc[j], __dmul_rn(rc, (in_n ? nxt_P[j] : rpb) - rpa));
+                        cur_acc[j] = on_c ? qc : cur_acc[j];
+                        nxt_acc[j] = on_n ? qn : nxt_acc[j];
+                    }
+                }
+                const bool in_next = e + 1 >= blk_first + kSgdBlock;
+                if (s_off == e + 1 - blk_first - (in_next ? kSgdBlock : 0)) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) s_next[(e + 1) & 1][3 * s_side + j] = in_next ? nxt_acc[j] : cur_acc[j];
                 }
             }
         }

@@ -34,21 +34,31 @@ def edge_arrays(pose_graph):
     """(a, b) int32 rows and 2x3 transforms of the edges the optimiser acts on, in the graph's
     iteration order.  Odometry edges (|a-b| == 1) are skipped by the reference (:14-16, :28-30) and
     edges with b <= a have empty node ranges (:20, :46), so neither is sent to the device."""
-    ab, tf = [], []
+    ab, Ts = [], []
     edges = pose_graph.graph.edges(data="object") if hasattr(pose_graph, "graph") else pose_graph
     for a, b, T in edges:
         a, b = int(a), int(b)
-        if abs(a - b) == 1 or b <= a:
+        if b - a <= 1:                                         # |a - b| == 1 or b <= a
             continue
-        T = np.asarray(T, dtype=np.float64)
-        if T.shape != (3, 3):
-            raise ValueError(f"edge ({a}, {b}) carries a transform of shape {T.shape}; expected (3, 3)")
-        if not (T[2, 0] == 0.0 and T[2, 1] == 0.0 and T[2, 2] == 1.0):
-            raise ValueError(f"edge ({a}, {b}): the transform's bottom row is not [0, 0, 1]")
         ab.append((a, b))
-        tf.append(T[:2, :].reshape(6))
+        Ts.append(T)
+    if not ab:
+        return np.zeros((0, 2), dtype=np.int32), np.zeros((0, 6), dtype=np.float64)
+    # one conversion and one check for all edges; the per-edge walk below only names the offender
+    try:
+        tf = np.asarray(Ts, dtype=np.float64)
+    except ValueError:
+        tf = None
+    if tf is None or tf.shape != (len(ab), 3, 3) or not (
+            (tf[:, 2, 0] == 0.0) & (tf[:, 2, 1] == 0.0) & (tf[:, 2, 2] == 1.0)).all():
+        for (a, b), T in zip(ab, Ts):
+            T = np.asarray(T, dtype=np.float64)
+            if T.shape != (3, 3):
+                raise ValueError(f"edge ({a}, {b}) carries a transform of shape {T.shape}; expected (3, 3)")
+            if not (T[2, 0] == 0.0 and T[2, 1] == 0.0 and T[2, 2] == 1.0):
+                raise ValueError(f"edge ({a}, {b}): the transform's bottom row is not [0, 0, 1]")
     return (np.asarray(ab, dtype=np.int32).reshape(-1, 2),
-            np.asarray(tf, dtype=np.float64).reshape(-1, 6))
+            np.ascontiguousarray(tf[:, :2, :]).reshape(-1, 6))
 
 
 def sgd_steps(poses, edges_ab, edges_T6, learning_rates, loop_closure_uncertainty=0.1, device=None):
