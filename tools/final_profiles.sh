@@ -16,4 +16,6 @@ ncu --set full --clock-control none --import-source on -k regex:icp_align_kernel
 cmd2="python tools/slam_pipeline.py --sgd-steps 2"
 $cmd2 > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"sgd_chain|proximity_closest" -c 3 -f -o gpurun_out/${tag}_sgd_prox $cmd2 > gpurun_out/ncu3.log 2>&1
+python tools/sgd_bench.py --profile > gpurun_out/${tag}_sgd_bench.json 2> gpurun_out/${tag}_sgd_kernels.txt
+python tools/slam_pipeline.py > gpurun_out/${tag}_slam_pipeline.json 2>> gpurun_out/${tag}_bench.err
 tail -2 gpurun_out/${tag}_gpu_tests.log; tail -c 400 gpurun_out/${tag}_bench.json

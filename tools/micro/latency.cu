@@ -23,7 +23,6 @@ __global__ void chain(double x0, double y0, int *idx, long long *out, double *si
         if (OP == 2) x = __dmul_rn(x, y);
         if (OP == 3) f = fmaf(f, g, g);
         if (OP == 4) k = s_next[k];
-        if (OP == 5) x = __shfl_xor_sync(0xffffffffu, x, 1);
         if (OP == 6) x = (double)(int)x + y;                      // F2I + I2F + DADD
         if (OP == 7) x = floor(x) + y;
         if (OP == 8) x = s_d[((int)__double2hiint(x)) & 255] + y;   // LDS.64 + DADD (address from the value)
@@ -59,7 +58,6 @@ int main()
     run<2>("DMUL", idx, out, sink);
     run<3>("FFMA", idx, out, sink);
     run<4>("LDS.32 pointer chase", idx, out, sink);
-    run<5>("SHFL (double = 2 SHFL)", idx, out, sink);
     run<6>("F2I.F64 + I2F.F64 + DADD", idx, out, sink);
     run<7>("floor(double) + DADD", idx, out, sink);
     run<8>("LDS.64 + DADD", idx, out, sink);
