@@ -190,3 +190,23 @@ def test_scan_list_helper_describes_a_list_of_arrays():
         gicp.ScanList([])
     t = gicp.ScanTable.from_lengths(sl.lens)
     assert t.n_scans == 257 and t.longest == int(sl.lens.max())
+
+
+def test_edge_arrays_keeps_what_the_optimiser_acts_on():
+    """Host side of the pose-graph SGD drop-in (no GPU needed): odometry edges (|a-b| == 1) and edges with
+    b <= a are left out (reference src/pose_graph_optimization.py:14-16, :20, :28-30, :46), iteration order
+    is kept, malformed transforms are named."""
+    from icp_slam_b200 import pose_graph_optimization as pgo
+    T = np.array([[0.0, -1.0, 2.0], [1.0, 0.0, 3.0], [0.0, 0.0, 1.0]])
+    edges = [(0, 1, np.eye(3)), (7, 3, np.eye(3)), (2, 9, T), (4, 5, np.eye(3)), (1, 6, np.eye(3)), (5, 5, np.eye(3))]
+    ab, T6 = pgo.edge_arrays(edges)
+    assert ab.dtype == np.int32 and ab.tolist() == [[2, 9], [1, 6]]
+    np.testing.assert_array_equal(T6, np.stack([T[:2].reshape(6), np.eye(3)[:2].reshape(6)]))
+    assert T6.flags["C_CONTIGUOUS"] and T6.dtype == np.float64
+    ab0, T0 = pgo.edge_arrays([(0, 1, np.eye(3))])
+    assert ab0.shape == (0, 2) and T0.shape == (0, 6)
+    bad = np.eye(3); bad[2, 0] = 0.5
+    with pytest.raises(ValueError, match=r"edge \(0, 3\).*bottom row"):
+        pgo.edge_arrays([(2, 9, T), (0, 3, bad)])
+    with pytest.raises(ValueError, match=r"edge \(0, 3\).*shape \(2, 2\)"):
+        pgo.edge_arrays([(0, 3, np.eye(2)), (2, 9, T)])
