@@ -148,8 +148,8 @@ __device__ __forceinline__ double mod_pos(double x, double m, double inv_m)
 // the next one.  Every iteration the owners add the newest record to both (two slots x three dofs,
 // no memory traffic but the record) and the owners of the next edge's endpoints publish them.  When
 // the chain enters a new block, every owner loads its slot of the block after it and catches it up
-// on all records so far in one burst -- records stream through L1 as broadcast loads of 16-byte
-// pairs from an array of 80-byte records, the running pose stays in registers.  Total work
+// on all records so far in one burst -- 80-byte records stream through shared-memory tiles (one
+// coalesced read per tile, fetched a tile ahead), the running pose stays in registers.  Total work
 // O(E^2 / 480) like any lazy scheme, but no reductions and no per-edge memory round trips, any E.
 // (Spreading the catch-up over the iterations of the block instead -- a few records per edge -- lost:
 // every iteration then waits for an L2 round trip that the burst amortises over hundreds of records.)
@@ -166,6 +166,7 @@ constexpr int kSgdThreads = 512;
 constexpr int kSgdWarps = kSgdThreads / 32;
 constexpr int kSgdOwners = kSgdThreads - 32;                   // threads that own slots (warps 1..15)
 constexpr int kSgdBlock = kSgdOwners / 2;                      // edges per block: one slot per owner and block
+constexpr int kSgdTile = kSgdOwners / 5;                       // records per catch-up tile: one 16-byte piece per owner
 
 struct SgdRecords {          // structure of arrays, E entries each (global memory; read by sgd_apply_kernel)
     int2   *ab;
@@ -219,6 +220,7 @@ sgd_chain_kernel(const SgdArgs a)
     __shared__ double s_wtot[3][kSgdWarps];
     __shared__ double s_next[2][6];                            // per edge parity: published poses of its endpoints
     __shared__ double s_coef[2][4];                            // per edge parity: the coefficients of its record
+    __shared__ double2 s_tile[2][kSgdOwners];                  // catch-up bursts: two tiles of kSgdTile 80-byte records
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -388,25 +390,38 @@ sgd_chain_kernel(const SgdArgs a)
             }
             if (e == blk_first + kSgdBlock) {
                 // ---- the chain enters the next block: its slots move up, the slots of the block after it
-                // are loaded and caught up on the records 0..e-2 (record e-1 follows below, as for all).
-                // Same address in every thread: broadcast loads of five 16-byte pairs per record ----
+                // are loaded and caught up on the records 0..e-2 (record e-1 follows below, as for all) ----
                 blk_first += kSgdBlock;
                 cur_node = nxt_node;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { cur_P[j] = nxt_P[j]; cur_acc[j] = nxt_acc[j]; }
                 slot_load(blk_first + kSgdBlock + s_off, nxt_node, nxt_P, nxt_acc);
-                if (nxt_node >= 0) {
-#pragma unroll 4
-                    for (int r = 0; r < e - 1; ++r) {
-                        const double2 *rec = reinterpret_cast<const double2 *>(a.RECA + 10 * (size_t)r);
-                        const double2 v0 = rec[0], v1 = rec[1], v2 = rec[2], v3 = rec[3], v4 = rec[4];
-                        const double rc[3] = {v0.x, v0.y, v1.x}, rpa[3] = {v1.y, v2.x, v2.y}, rpb[3] = {v3.x, v3.y, v4.x};
-                        const int ra = __double2loint(v4.y), rb = __double2hiint(v4.y);
-                        const bool on = nxt_node > ra, inside = nxt_node <= rb;
+                // The records stream through shared memory in tiles of kSgdTile: thread `own` fetches 16-byte
+                // piece `own` of the tile (one coalesced 7.5 KB read per tile, issued one tile ahead), then
+                // everybody reads the tile as broadcast loads.  One named barrier per tile among the owners.
+                const int n_rec = e - 1;
+                const double2 *src = reinterpret_cast<const double2 *>(a.RECA);
+                const int n_piece = 5 * n_rec;                               // 16-byte pieces in records 0..n_rec-1
+                double2 stage = own < n_piece ? src[own] : make_double2(0.0, 0.0);
+                for (int t0 = 0, buf = 0; t0 < n_rec; t0 += kSgdTile, buf ^= 1) {
+                    s_tile[buf][own] = stage;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kSgdOwners) : "memory");
+                    const int nxt_piece = 5 * (t0 + kSgdTile) + own;
+                    if (nxt_piece < n_piece) stage = src[nxt_piece];
+                    const int cnt = min(kSgdTile, n_rec - t0);
+                    if (nxt_node >= 0) {
+#pragma unroll 2
+                        for (int r = 0; r < cnt; ++r) {
+                            const double2 *rec = &s_tile[buf][5 * r];
+                            const double2 v0 = rec[0], v1 = rec[1], v2 = rec[2], v3 = rec[3], v4 = rec[4];
+                            const double rc[3] = {v0.x, v0.y, v1.x}, rpa[3] = {v1.y, v2.x, v2.y}, rpb[3] = {v3.x, v3.y, v4.x};
+                            const int ra = __double2loint(v4.y), rb = __double2hiint(v4.y);
+                            const bool on = nxt_node > ra, inside = nxt_node <= rb;
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            const double q = __dadd_rn(nxt_acc[j], __dmul_rn(rc[j], (inside ? nxt_P[j] : rpb[j]) - rpa[j]));
-                            nxt_acc[j] = on ? q : nxt_acc[j];
+                            for (int j = 0; j < 3; ++j) {
+                                const double q = __dadd_rn(nxt_acc[j], __dmul_rn(rc[j], (inside ? nxt_P[j] : rpb[j]) - rpa[j]));
+                                nxt_acc[j] = on ? q : nxt_acc[j];
+                            }
                         }
                     }
                 }
