@@ -11,14 +11,14 @@
 // Pass (2) is order dependent -- an edge reads poses that earlier edges moved -- so it stays a
 // sequential chain over the edges, but the O(N) inner loops per edge are data parallel:
 //   * sgd_weights_kernel: one thread per edge computes its diagonal (E sin/cos pairs);
-//   * sgd_accumulate_kernel: one thread per node adds the diagonals of the edges covering it, in
+//   * sgd_accumulate_kernel: one thread per (node, dof) adds the diagonals of the edges covering it, in
 //     edge order (the reference's order of additions, so M has the reference's bits given the
 //     same diagonals); the edge list streams through shared memory;
 //   * sgd_chain_kernel: ONE CTA walks the edges lazily: every edge leaves a record, and only the
 //     endpoints of the edges still to come are kept up to date (see the kernel's own comment);
 //     node i > a receives beta_j/total_j * (P_j[min(i,b)] - P_j[a]) -- the
 //     reference's running sum `dpose` in closed form over the prefix sums P_j[i] = sum_{k<=i} 1/M[k,j];
-//   * sgd_apply_kernel: one thread per node applies all records, in edge order.
+//   * sgd_apply_kernel: one thread per (node, dof) applies all records, in edge order.
 // All arithmetic is fp64; the results agree with the reference to rounding (the 3x3 inverses are
 // evaluated in closed form, the running sums as prefix differences); tests/test_gpu_sgd.py pins
 // them to 1e-9 against goldens of the unmodified reference.
@@ -179,18 +179,6 @@ __device__ __forceinline__ SgdRecords sgd_records(const SgdArgs &a)
     r.coef = a.REC; r.pa = a.REC + 3 * (size_t)a.E; r.pb = a.REC + 6 * (size_t)a.E;
     r.ab = reinterpret_cast<int2 *>(a.REC + 9 * (size_t)a.E);
     return r;
-}
-
-// f_e(i) for one record and one node, added to acc[3] (product and sum rounded separately, like the
-// reference's `dpose += ...; poses[i] += dpose`)
-__device__ __forceinline__ void sgd_add_term(int i, const double *Pi, int ra, int rb, const double *coef,
-                                             const double *pa, const double *pb, double *acc)
-{
-    if (i > ra) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            acc[j] = __dadd_rn(acc[j], __dmul_rn(coef[j], (i <= rb ? Pi[j] : pb[j]) - pa[j]));
-    }
 }
 
 // Everything edge e needs that does not depend on the moving poses, gathered once per pass into one
