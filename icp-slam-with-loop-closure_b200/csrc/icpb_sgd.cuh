@@ -215,6 +215,9 @@ sgd_chain_kernel(const SgdArgs a)
     const SgdRecords R = sgd_records(a);
     SgdEdgeFull *ES = reinterpret_cast<SgdEdgeFull *>(a.ES);
 
+#ifdef ICPB_SGD_PROBE
+    const long long pq0 = clock64();
+#endif
     // ---- gamma: the first edge with the smallest |diag(W)|^2 (strict > in :23) ----
     {
         double best = inf;
@@ -237,21 +240,29 @@ sgd_chain_kernel(const SgdArgs a)
             for (int j = 0; j < 3; ++j) s_gamma[j] = any ? a.dW[4 * be + j] : inf;
         }
     }
+#ifdef ICPB_SGD_PROBE
+    const long long pq1 = clock64();
+    long long pq2 = 0, pq3 = 0, pq4 = 0;
+#endif
     // ---- P_j[i] = sum_{k <= i} 1/M[k,j]: contiguous slices per thread, then the slice offsets ----
     {
+        // (M is read-only here -- __ldg -- and nothing is stored in this loop, so the loads pipeline; with
+        // P written in the same loop every load waited for the store before it: an L2 round trip per value)
         const int L = (n + NT - 1) / NT;
         const int i0 = min(tid * L, n), i1 = min(i0 + L, n);
         double acc[3] = {0.0, 0.0, 0.0};
         for (int i = i0; i < i1; ++i)
             for (int j = 0; j < 3; ++j) {
-                const double m = a.M[3 * i + j];
+                const double m = __ldg(a.M + 3 * i + j);
                 acc[j] += m > 0.0 ? 1.0 / m : 0.0;             // uncovered nodes never enter a range
-                a.P[3 * i + j] = acc[j];
             }
         // exclusive scan of the slice totals over the threads in two levels, each a sequential fold in a
         // fixed order (lane 0..2 of every warp over its 32 totals, one dof each; then the 16 warp totals)
         for (int j = 0; j < 3; ++j) s_scan[j][tid] = acc[j];
         __syncthreads();
+#ifdef ICPB_SGD_PROBE
+        pq2 = clock64();
+#endif
         if (lane < 3) {
             double run = 0.0;
             for (int t = warp * 32; t < warp * 32 + 32; ++t) { const double v = s_scan[lane][t]; s_scan[lane][t] = run; run += v; }
@@ -263,22 +274,40 @@ sgd_chain_kernel(const SgdArgs a)
             for (int w = 0; w < kSgdWarps; ++w) { const double v = s_wtot[tid][w]; s_wtot[tid][w] = run; run += v; }
         }
         __syncthreads();
-        for (int i = i0; i < i1; ++i)
-            for (int j = 0; j < 3; ++j) a.P[3 * i + j] += s_wtot[j][warp] + s_scan[j][tid];
+        {
+            double run[3];
+            for (int j = 0; j < 3; ++j) run[j] = s_wtot[j][warp] + s_scan[j][tid];
+            for (int i = i0; i < i1; ++i)                      // second walk over the slice, from its offset
+                for (int j = 0; j < 3; ++j) {
+                    const double m = __ldg(a.M + 3 * i + j);
+                    run[j] += m > 0.0 ? 1.0 / m : 0.0;
+                    a.P[3 * i + j] = run[j];
+                }
+        }
         __syncthreads();
+#ifdef ICPB_SGD_PROBE
+        pq3 = clock64();
+#endif
         // ---- per edge: everything the chain needs in one struct, the static part of its record ----
         for (int e = tid; e < a.E; e += NT) {
-            const int ea = a.edges[2 * e], eb = a.edges[2 * e + 1];
+            // every load before the first store (the compiler has to assume that the outputs overlap the inputs)
+            const int ea = __ldg(a.edges + 2 * e), eb = __ldg(a.edges + 2 * e + 1);
+            const double t0 = __ldg(a.tf + 6 * e), t2 = __ldg(a.tf + 6 * e + 2), t3 = __ldg(a.tf + 6 * e + 3), t5 = __ldg(a.tf + 6 * e + 5);
+            double pa[3], pb[3], q0a[3], q0b[3];
+            for (int j = 0; j < 3; ++j) {
+                pa[j] = a.P[3 * ea + j]; pb[j] = a.P[3 * eb + j];
+                q0a[j] = a.poses[3 * ea + j]; q0b[j] = a.poses[3 * eb + j];
+            }
             SgdEdgeFull x;
             x.ea = ea; x.eb = eb; x.span = (double)(eb - ea);
-            x.t2 = a.tf[6 * e + 2]; x.t5 = a.tf[6 * e + 5];
-            x.phi = atan2(a.tf[6 * e + 3], a.tf[6 * e]);
+            x.t2 = t2; x.t5 = t5;
+            x.phi = atan2(t3, t0);
             for (int j = 0; j < 3; ++j) {
-                const double pa = a.P[3 * ea + j], pb = a.P[3 * eb + j], tot = pb - pa;
-                x.base[j] = pa; x.total[j] = tot; x.itot[j] = 1.0 / tot; x.Pb[j] = pb;
-                x.p0a[j] = a.poses[3 * ea + j]; x.p0b[j] = a.poses[3 * eb + j];
-                R.pa[j * (size_t)a.E + e] = pa; R.pb[j * (size_t)a.E + e] = pb;
+                const double tot = pb[j] - pa[j];
+                x.base[j] = pa[j]; x.total[j] = tot; x.itot[j] = 1.0 / tot; x.Pb[j] = pb[j];
+                x.p0a[j] = q0a[j]; x.p0b[j] = q0b[j];
             }
+            for (int j = 0; j < 3; ++j) { R.pa[j * (size_t)a.E + e] = pa[j]; R.pb[j * (size_t)a.E + e] = pb[j]; }
             ES[e] = x;
             R.ab[e] = make_int2(ea, eb);
             double *ra = a.RECA + 10 * (size_t)e;                // {coef[3] (written by the chain), pa[3], pb[3], (a, b)}
@@ -289,6 +318,9 @@ sgd_chain_kernel(const SgdArgs a)
         }
     }
     __syncthreads();
+#ifdef ICPB_SGD_PROBE
+    pq4 = clock64();
+#endif
     // step factors that do not depend on the moving poses: alpha_j = lr / gamma_j (:39-40)
     double alpha[3];
     for (int j = 0; j < 3; ++j) alpha[j] = (1.0 / s_gamma[j]) * a.learning_rate;
@@ -439,7 +471,7 @@ sgd_chain_kernel(const SgdArgs a)
         __syncthreads();           // record e, the endpoints of edge e+1 and the struct of edge e+2 are visible
     }
 #ifdef ICPB_SGD_PROBE
-    if (tid == 0) printf("sgd probe: loop %lld cycles, E %d\n", clock64() - pr_begin, a.E);
+    if (tid == 0) printf("sgd probe: loop %lld cycles, E %d; prologue: gamma %lld, P local %lld, scan+offsets %lld, edge structs %lld, ring %lld\n", clock64() - pr_begin, a.E, pq1 - pq0, pq2 - pq1, pq3 - pq2, pq4 - pq3, pr_begin - pq4);
 #endif
 }
 
