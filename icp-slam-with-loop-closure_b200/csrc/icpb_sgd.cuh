@@ -40,7 +40,7 @@ struct SgdArgs {
     double        *P;         // n x 3 scratch: inclusive prefix sums of 1/M
     double        *REC;       // E x 10 scratch: the per-edge records of the lazy chain (SgdRecords)
     double        *RECA;      // E x 10 scratch: the same records as an array of structs (the chain's catch-up bursts)
-    double        *ES;        // E x 23 scratch: the per-edge inputs of the chain (SgdEdgeFull)
+    double        *ES;        // 23 x E scratch: the per-edge inputs of the chain (the fields of SgdEdgeFull, one array each)
 };
 
 // the optimiser ignores odometry edges (src/pose_graph_optimization.py:14-16, :28-30)
@@ -182,7 +182,8 @@ __device__ __forceinline__ SgdRecords sgd_records(const SgdArgs &a)
 }
 
 // Everything edge e needs that does not depend on the moving poses, gathered once per pass into one
-// contiguous 184-byte struct and handed to the chain through a ring in shared memory.
+// 184-byte struct (stored field by field in global memory) and handed to the chain through a ring in
+// shared memory.
 struct SgdEdgeFull {
     int ea, eb;                   // node ids
     double span;                  // (double)(eb - ea)
@@ -213,7 +214,10 @@ sgd_chain_kernel(const SgdArgs a)
     const int n = a.n;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const SgdRecords R = sgd_records(a);
-    SgdEdgeFull *ES = reinterpret_cast<SgdEdgeFull *>(a.ES);
+    // field f of edge e (SgdEdgeFull seen as 23 doubles) lives at ES[f * E + e]: the threads of a warp fill
+    // the structs of 32 consecutive edges with coalesced stores
+    double *ES = a.ES;
+    const size_t ES_stride = (size_t)a.E;
 
 #ifdef ICPB_SGD_PROBE
     const long long pq0 = clock64();
@@ -308,7 +312,11 @@ sgd_chain_kernel(const SgdArgs a)
                 x.p0a[j] = q0a[j]; x.p0b[j] = q0b[j];
             }
             for (int j = 0; j < 3; ++j) { R.pa[j * (size_t)a.E + e] = pa[j]; R.pb[j * (size_t)a.E + e] = pb[j]; }
-            ES[e] = x;
+            {
+                const double *xd = reinterpret_cast<const double *>(&x);
+#pragma unroll
+                for (int f = 0; f < kSgdEdgeDoubles; ++f) ES[f * ES_stride + e] = xd[f];
+            }
             R.ab[e] = make_int2(ea, eb);
             double *ra = a.RECA + 10 * (size_t)e;                // {coef[3] (written by the chain), pa[3], pb[3], (a, b)}
             for (int j = 0; j < 3; ++j) { ra[3 + j] = x.base[j]; ra[6 + j] = x.Pb[j]; }
@@ -334,8 +342,8 @@ sgd_chain_kernel(const SgdArgs a)
     double es_staged = 0.0;                                    // double `lane` of the struct of edge e + 2
     if (warp == kSgdWarps - 1 && lane < kSgdEdgeDoubles) {
         for (int k = 0; k < 2 && k < a.E; ++k)
-            reinterpret_cast<double *>(&s_es[k])[lane] = reinterpret_cast<const double *>(ES + k)[lane];
-        if (2 < a.E) es_staged = reinterpret_cast<const double *>(ES + 2)[lane];
+            reinterpret_cast<double *>(&s_es[k])[lane] = ES[lane * ES_stride + k];
+        if (2 < a.E) es_staged = ES[lane * ES_stride + 2];
     }
     __syncthreads();
     // Scalar warp, lane-parallel: lane l < 6 carries dof j = l % 3 of endpoint side = l / 3 (0: a, 1: b);
@@ -353,10 +361,13 @@ sgd_chain_kernel(const SgdArgs a)
     auto slot_load = [&](int edge, int &node, double *P, double *acc) {
         node = -1;
         if (warp >= 1 && edge < a.E) {
-            const SgdEdgeFull &x = ES[edge];
-            node = s_side ? x.eb : x.ea;
+            const double ab = ES[edge];                                        // field 0: (ea, eb) as two ints
+            node = s_side ? __double2hiint(ab) : __double2loint(ab);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) { P[j] = s_side ? x.Pb[j] : x.base[j]; acc[j] = s_side ? x.p0b[j] : x.p0a[j]; }
+            for (int j = 0; j < 3; ++j) {
+                P[j] = ES[((s_side ? kEsPb : kEsBase) + j) * ES_stride + edge];
+                acc[j] = ES[((s_side ? kEsP0b : kEsP0a) + j) * ES_stride + edge];
+            }
         }
     };
     slot_load(s_off, cur_node, cur_P, cur_acc);
@@ -406,7 +417,7 @@ sgd_chain_kernel(const SgdArgs a)
             if (warp == kSgdWarps - 1 && lane < kSgdEdgeDoubles && e + 2 < a.E) {
                 // ring slot (e + 2) % 4 was last read in iteration e - 1 (as the previous edge of e - 1's successor)
                 reinterpret_cast<double *>(&s_es[(e + 2) & 3])[lane] = es_staged;
-                if (e + 3 < a.E) es_staged = reinterpret_cast<const double *>(ES + e + 3)[lane];
+                if (e + 3 < a.E) es_staged = ES[lane * ES_stride + e + 3];
             }
             if (e == blk_first + kSgdBlock) {
                 // ---- the chain enters the next block: its slots move up, the slots of the block after it
