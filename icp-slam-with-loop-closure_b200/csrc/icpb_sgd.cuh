@@ -205,7 +205,6 @@ sgd_chain_kernel(const SgdArgs a)
     __shared__ double s_best[32];
     __shared__ int    s_beste[32];
     __shared__ double s_gamma[3];
-    __shared__ double s_scan[3][kSgdThreads];
     __shared__ double s_wtot[3][kSgdWarps];
     __shared__ double s_next[2][6];                            // per edge parity: published poses of its endpoints
     __shared__ double s_coef[2][4];                            // per edge parity: the coefficients of its record
@@ -246,49 +245,45 @@ sgd_chain_kernel(const SgdArgs a)
     }
 #ifdef ICPB_SGD_PROBE
     const long long pq1 = clock64();
-    long long pq2 = 0, pq3 = 0, pq4 = 0;
+    long long pq3 = 0, pq4 = 0;
 #endif
-    // ---- P_j[i] = sum_{k <= i} 1/M[k,j]: contiguous slices per thread, then the slice offsets ----
+    // ---- P_j[i] = sum_{k <= i} 1/M[k,j]: chunks of NT consecutive nodes, one node per thread (coalesced
+    // loads and stores; thread-contiguous slices cost a sector per value), an inclusive scan per chunk
+    // -- shuffles within a warp, the warp totals through shared memory, both in a fixed order -- on top of
+    // the running total of the chunks before it.  The next chunk's M is fetched before this one is scanned.
     {
-        // (M is read-only here -- __ldg -- and nothing is stored in this loop, so the loads pipeline; with
-        // P written in the same loop every load waited for the store before it: an L2 round trip per value)
-        const int L = (n + NT - 1) / NT;
-        const int i0 = min(tid * L, n), i1 = min(i0 + L, n);
-        double acc[3] = {0.0, 0.0, 0.0};
-        for (int i = i0; i < i1; ++i)
-            for (int j = 0; j < 3; ++j) {
-                const double m = __ldg(a.M + 3 * i + j);
-                acc[j] += m > 0.0 ? 1.0 / m : 0.0;             // uncovered nodes never enter a range
-            }
-        // exclusive scan of the slice totals over the threads in two levels, each a sequential fold in a
-        // fixed order (lane 0..2 of every warp over its 32 totals, one dof each; then the 16 warp totals)
-        for (int j = 0; j < 3; ++j) s_scan[j][tid] = acc[j];
-        __syncthreads();
-#ifdef ICPB_SGD_PROBE
-        pq2 = clock64();
-#endif
-        if (lane < 3) {
-            double run = 0.0;
-            for (int t = warp * 32; t < warp * 32 + 32; ++t) { const double v = s_scan[lane][t]; s_scan[lane][t] = run; run += v; }
-            s_wtot[lane][warp] = run;
-        }
-        __syncthreads();
-        if (tid < 3) {
-            double run = 0.0;
-            for (int w = 0; w < kSgdWarps; ++w) { const double v = s_wtot[tid][w]; s_wtot[tid][w] = run; run += v; }
-        }
-        __syncthreads();
-        {
-            double run[3];
-            for (int j = 0; j < 3; ++j) run[j] = s_wtot[j][warp] + s_scan[j][tid];
-            for (int i = i0; i < i1; ++i)                      // second walk over the slice, from its offset
+        double carry[3] = {0.0, 0.0, 0.0};
+        double mn[3];
+        for (int j = 0; j < 3; ++j) mn[j] = tid < n ? __ldg(a.M + 3 * tid + j) : 0.0;
+        for (int c0 = 0; c0 < n; c0 += NT) {
+            const int i = c0 + tid;
+            double v[3];
+            for (int j = 0; j < 3; ++j) v[j] = mn[j] > 0.0 ? 1.0 / mn[j] : 0.0;   // uncovered nodes never enter a range
+            if (c0 + NT < n)
+                for (int j = 0; j < 3; ++j) mn[j] = i + NT < n ? __ldg(a.M + 3 * (i + NT) + j) : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    const double m = __ldg(a.M + 3 * i + j);
-                    run[j] += m > 0.0 ? 1.0 / m : 0.0;
-                    a.P[3 * i + j] = run[j];
+                    const double t = __shfl_up_sync(0xffffffffu, v[j], o);
+                    if (lane >= o) v[j] += t;
                 }
+            if (lane == 31)
+                for (int j = 0; j < 3; ++j) s_wtot[j][warp] = v[j];
+            __syncthreads();
+            double off[3], tot[3];
+            for (int j = 0; j < 3; ++j) { off[j] = carry[j]; tot[j] = carry[j]; }
+            for (int w = 0; w < kSgdWarps; ++w)
+                for (int j = 0; j < 3; ++j) {
+                    const double t = s_wtot[j][w];
+                    tot[j] += t;
+                    if (w < warp) off[j] += t;
+                }
+            if (i < n)
+                for (int j = 0; j < 3; ++j) a.P[3 * i + j] = off[j] + v[j];
+            for (int j = 0; j < 3; ++j) carry[j] = tot[j];
+            __syncthreads();                                   // s_wtot is rewritten by the next chunk
         }
-        __syncthreads();
 #ifdef ICPB_SGD_PROBE
         pq3 = clock64();
 #endif
@@ -482,7 +477,7 @@ sgd_chain_kernel(const SgdArgs a)
         __syncthreads();           // record e, the endpoints of edge e+1 and the struct of edge e+2 are visible
     }
 #ifdef ICPB_SGD_PROBE
-    if (tid == 0) printf("sgd probe: loop %lld cycles, E %d; prologue: gamma %lld, P local %lld, scan+offsets %lld, edge structs %lld, ring %lld\n", clock64() - pr_begin, a.E, pq1 - pq0, pq2 - pq1, pq3 - pq2, pq4 - pq3, pr_begin - pq4);
+    if (tid == 0) printf("sgd probe: loop %lld cycles, E %d; prologue: gamma %lld, P %lld, edge structs %lld, ring %lld\n", clock64() - pr_begin, a.E, pq1 - pq0, pq3 - pq1, pq4 - pq3, pr_begin - pq4);
 #endif
 }
 
