@@ -104,6 +104,37 @@ def test_random_graphs_against_the_oracle(n, n_loops, seed):
     np.testing.assert_allclose(pg.poses, want, **TOL)
 
 
+@pytest.mark.parametrize("n_edges", [95, 96, 97, 239, 240, 241, 242, 479, 480, 481, 577])
+def test_edge_counts_around_the_chain_block_and_tile_sizes(n_edges):
+    """The chain kernel cuts the edges into blocks of 240 (one slot per owner thread and block) and
+    catches slots up in tiles of 96 records: edge counts on and next to those sizes, against the numpy
+    restatement."""
+    from icp_slam_b200 import pose_graph_optimization as pgo, synth
+    from oracle import slam_oracle
+    n = 900
+    rng = np.random.default_rng(1000 + n_edges)
+    truth = synth.loop_trajectory(n, step=60.0 / n)
+    poses = truth + np.cumsum(rng.normal(0, [2e-3, 2e-3, 1e-3], (n, 3)), axis=0)
+    loops, seen = [], set()
+    while len(loops) < n_edges:
+        a, b = sorted(int(v) for v in rng.choice(n, 2, replace=False))
+        # no edge twice, as in the reference's DiGraph: the second copy of an edge finds a residual of
+        # rounding noise, whose heading component `% (2 pi)` puts at 0 or at 2 pi (src/pose_graph_optimization.py:35)
+        if b - a < 2 or (a, b) in seen:
+            continue
+        seen.add((a, b))
+        rel = np.linalg.inv(synth.pose_to_mat(truth[a])) @ synth.pose_to_mat(truth[b])
+        loops.append((a, b, rel))
+    loops = slam_oracle.graph_order(loops)
+    assert len(loops) == n_edges
+    pg = Graph(poses.copy(), loops)
+    want = poses.copy()
+    for k in range(2):
+        slam_oracle.sgd_step(want, loops, learning_rate=1 / float(k + 1), in_graph_order=True)
+    pgo.optimise(pg, 2)
+    np.testing.assert_allclose(pg.poses, want, **TOL)
+
+
 def test_repeated_calls_give_the_same_bits():
     """The lazy chain adds its partial sums in a fixed order: two calls, same bits."""
     from icp_slam_b200 import pose_graph_optimization as pgo
